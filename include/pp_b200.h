@@ -1,0 +1,147 @@
+/*
+ * pp_b200.h -- C ABI of the B200-native Monte Carlo engine for the PatchyParticles hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handle, host pointers and sizes only.  Every entry
+ * point names the reference interface it replaces (paths relative to the PatchyParticles tree).
+ * The reference's plugin points are the two function pointers System.do_ensemble / do_dynamics
+ * (defs.h:77-78) bound in MC_init (MC.c:85-131) and called once per MC step from main.c:119; the
+ * GPU engine replaces the whole do_ensemble body (sweep granularity).  INTEGRATION.md shows the
+ * binding a PatchyParticles maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; pp_last_error() gives the message
+ *     (the reference's convention is log-and-exit(1), output.c:374-388: the host maps non-zero
+ *     to exactly that).
+ *   - host arrays are caller-owned and copied; particle order on the ABI is always the caller's
+ *     original order (the engine keeps particles cell-sorted internally).
+ *   - positions r[N][3] and orientation matrices orient[N][3][3] are FP64, row-major, with the
+ *     meaning of PatchyParticle.r / .orientation (defs.h:47-56).
+ *   - a handle is not thread-safe; one handle drives one GPU (one slab of a multi-GPU run).
+ *   - there is no CPU fallback: without a CUDA device pp_create fails.
+ */
+#ifndef PP_B200_H_
+#define PP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+
+/* move-type slots of System.tries[] / accepted[] (defs.h:11-19) */
+#define PP_N_MOVES 8
+#define PP_ROTO_TRASL 0
+#define PP_VOLUME 6
+#define PP_LX 7
+
+/* ensembles (defs.h:21-25); only NVT and NPT are on the GPU path */
+#define PP_NVT 0
+#define PP_NPT 5
+
+typedef struct pp_handle pp_handle;
+
+/* Input-file keys of the hot path (system.c:61-196), same meaning and units. */
+typedef struct pp_params {
+	int ensemble;               /* Ensemble: PP_NVT or PP_NPT                       system.c:62 */
+	double temperature;         /* Temperature                                      system.c:66 */
+	double disp_max;            /* Disp_max                                         system.c:64 */
+	double theta_max;           /* Theta_max                                        system.c:65 */
+	double kf_delta;            /* KF_delta                                         system.c:83 */
+	double kf_cosmax;           /* KF_cosmax                                        system.c:84 */
+	double P;                   /* P (NPT)                                          system.c:168 */
+	double rescale_factor_max;  /* rescale_factor_max (NPT)                         system.c:167 */
+	int Lx_move;                /* Lx_move (NVT only, as in the reference)          system.c:171 */
+	double Lx_change_max;       /* Lx_change_max                                    system.c:177 */
+	double Lyz_min, Lyz_max;    /* Lyz_min / Lyz_max (absolute lengths)             system.c:178-179 */
+	int Lx_reference_sign;      /* 1: reproduce exp(+dE/T) of MC.c:562; 0: Metropolis exp(-dE/T) */
+	uint64_t seed;              /* Seed                                             system.c:71-75 */
+	int device;                 /* CUDA device ordinal */
+	int lanes_per_cell;         /* sweep-kernel tile width: 0 = default; 4, 8, 16 or 32 */
+	int use_graph;              /* 1: replay the per-sweep launch sequence as a CUDA graph */
+} pp_params;
+
+typedef struct pp_observables {
+	long long step;                      /* sweeps done since pp_upload */
+	int N;
+	double box[3];                       /* System.box                                  defs.h:60 */
+	double energy;                       /* System.energy = -(bonded pairs)             defs.h:65 */
+	long long tries[PP_N_MOVES];         /* System.tries   (int in the reference)       defs.h:95 */
+	long long accepted[PP_N_MOVES];      /* System.accepted                             defs.h:96 */
+	/* checkerboard bookkeeping (DESIGN.md "acceptance estimator") */
+	long long confined;                  /* proposals rejected for leaving their cell (no energy evaluated) */
+	long long overlapped;                /* proposals rejected by a hard-core overlap */
+	double acceptance_roto;              /* estimator of the reference's accepted/tries for ROTO_TRASL */
+	long long pair_checks;               /* pair tests executed by the sweep kernel */
+	int n_side[3];                       /* current (even) cell grid */
+} pp_observables;
+
+void pp_default_params(pp_params *p);
+int pp_abi_version(void);
+
+/* system_init + MC_init (system.c:58-252, MC.c:85-131): allocate an engine for one GPU. */
+int pp_create(const pp_params *params, pp_handle **out);
+int pp_destroy(pp_handle *h);                           /* system_free, system.c:254-276 */
+const char *pp_last_error(const pp_handle *h);          /* output_exit message, output.c:374-388 */
+
+/* The configuration read from Initial_conditions_file (system.c:213-245) goes to the GPU; builds the
+ * cell structure (cells_init + cells_fill, cells.c:17-63) as a counting sort.  Resets step/counters.
+ * The running energy is NOT computed here (main.c:55-61 does that explicitly: call pp_total_bonds). */
+int pp_upload(pp_handle *h, int N, const double *box, const double *r, const double *orient);
+/* particles[i].r / .orientation as output_save reads them (output.c:302-317), original order */
+int pp_download(pp_handle *h, double *r, double *orient);
+
+/* 0.5 * sum_i MC_energy(i) with the overlap flag (main.c:55-61, MC.c:488-495, 556-560, 769-776).
+ * bonds = number of bonded pairs (energy = -bonds).  Also (re)sets the running energy. */
+int pp_total_bonds(pp_handle *h, long long *bonds, int *overlap);
+/* per-particle bonded-neighbour counts, what Print_bonds reports (output.c:213-268) */
+int pp_bond_counts(pp_handle *h, int *counts);
+
+/* do_ensemble x nsteps (main.c:119 -> do_NVT / do_NPT, MC.c:19-29,60-68): each step is N
+ * roto-translation attempts (MC_move_rototranslate, MC.c:311-340) as one 8-colour checkerboard
+ * sweep, plus Binomial(N, 1/N) volume moves (NPT, MC.c:450-513) or Lx moves (NVT + Lx_move,
+ * MC.c:515-585).  Asynchronous: returns after enqueueing unless a box move needs a host decision. */
+int pp_sweep(pp_handle *h, long long nsteps);
+int pp_sync(pp_handle *h);
+
+/* what output_print reads from System (output.c:119-196); reset != 0 zeroes tries/accepted the way
+ * utils_reset_acceptance_counters does after each print (output.c:189). */
+int pp_get_observables(pp_handle *h, pp_observables *obs, int reset);
+
+/* MC_check_energy + cells_check (MC.c:766-784, cells.c:65-76): recompute the bond count from
+ * scratch, re-orthonormalise every orientation (gram_schmidt, utils.c:91-113), verify the cell
+ * population.  *ok = 0 if the running energy drifted by more than 1e-5 relative or an overlap
+ * exists; the running energy is then replaced by the recomputed one, as in the reference. */
+int pp_check_energy(pp_handle *h, long long *bonds_scratch, int *overlap, int *ok);
+
+/* Test hook: MC.c:328-335 on a list of proposals.  commit == 0: all against the frozen current
+ * configuration; commit != 0: sequential move list (accepted proposals are applied).
+ * dE[k] = reference deltaE (E_new = 0 when the new position overlaps), overlap[k], accept[k]. */
+int pp_eval_proposals(pp_handle *h, int n, const int *idx, const double *disp, const double *orient_new,
+		const double *u, int commit, int *dE, int *overlap, int *accept);
+
+/* Test hooks: one MC_change_volume (MC.c:450-513) / MC_change_Lx (MC.c:515-585) with the uniforms
+ * the reference would draw, in its draw order.  *accepted: 1 yes, 0 no, -1 early reject (Lx only). */
+int pp_volume_move(pp_handle *h, double u_dir, double u_vol, double u_acc, int *accepted);
+int pp_Lx_move(pp_handle *h, double u_lx, double u_acc, int *accepted);
+
+/* Plumbing for measurement: run on a caller-owned CUDA stream (cudaStream_t as void*), per-kernel
+ * CUDA-event timing, launch counting. */
+int pp_set_stream(pp_handle *h, void *cuda_stream);
+int pp_set_profiling(pp_handle *h, int enable);
+/* kernel classes for pp_kernel_stats */
+#define PP_K_CELLS 0     /* K1: cell build (count, scan, scatter, order, gather) */
+#define PP_K_SWEEP 1     /* K2: checkerboard sweep colour passes */
+#define PP_K_BONDS 2     /* K3: full bond count */
+#define PP_K_RESCALE 3   /* K4: position rescale */
+#define PP_K_PROPOSALS 4 /* K5: proposal evaluator */
+#define PP_K_ORTHO 5     /* K6: re-orthonormalise */
+#define PP_K_CLASSES 6
+int pp_kernel_stats(pp_handle *h, int kclass, long long *launches, double *ms_total);
+int pp_reset_kernel_stats(pp_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PP_B200_H_ */

@@ -1,0 +1,336 @@
+// pp_bonds.cu -- K3 (full bond count), per-particle bond counts, K4 (rescale), K5 (proposal
+// evaluator), K6 (re-orthonormalise) and the upload/download packers.
+#include "pp_kernels.cuh"
+
+namespace pp {
+
+constexpr int kBondThreads = 128;
+
+// ---------------------------------------------------------------------------------------------
+// K3: number of bonded pairs + overlap flag.  Replaces the total-energy loops of main.c:55-61,
+// MC.c:488-495, MC.c:556-560 and MC.c:769-776 (0.5 * sum_i MC_energy(i)).  One tile of G lanes
+// per cell; every unordered pair is tested once (slot_q > slot_p), which is exact because the
+// reference's pair test is antisymmetric in (p, q) operation by operation.  Lane-local integer
+// counts are reduced per block in shared memory, then one atomic per block.
+// ---------------------------------------------------------------------------------------------
+template<int G>
+__global__ void __launch_bounds__(kBondThreads) k_total_bonds(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
+		const double4 *__restrict__ pos, const double *__restrict__ ori, Counters *__restrict__ counters) {
+	constexpr int kTiles = kBondThreads / G;
+	__shared__ Neighbourhood s_nb[kTiles];
+	__shared__ int s_bonds, s_overlap;
+	cg::thread_block block = cg::this_thread_block();
+	cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
+	const int tile_in_block = threadIdx.x / G;
+	const int lane = tile.thread_rank();
+	if(threadIdx.x == 0) {
+		s_bonds = 0;
+		s_overlap = 0;
+	}
+	__syncthreads();
+
+	int bonds = 0, overlap = 0;
+	const int nyz = sc.n_side[1] * sc.n_side[2];
+	for(int cell = blockIdx.x * kTiles + tile_in_block; cell < sc.n_cells; cell += gridDim.x * kTiles) {
+		const int first = cell_start[cell], last = cell_start[cell + 1];
+		if(first == last) continue;
+		const int ix = cell / nyz, iy = (cell - ix * nyz) / sc.n_side[2], iz = cell - ix * nyz - iy * sc.n_side[2];
+		Neighbourhood &nb = s_nb[tile_in_block];
+		tile.sync();
+		const int total = build_neighbourhood<G>(tile, sc, cell_start, ix, iy, iz, nb);
+		for(int sp = first; sp < last; sp++) {
+			const double4 p4 = pos[sp];
+			const Vec3 p = {p4.x, p4.y, p4.z};
+			double mp[9], pp[12];
+#pragma unroll
+			for(int k = 0; k < 9; k++) mp[k] = ori[9ll * sp + k];
+			patches_from(sc.base, mp, pp);
+			for(int j = lane; j < total; j += G) {
+				const int sq = neighbour_slot(nb, j);
+				if(sq <= sp) continue;
+				const int v = pair_test(sc, p, pp, pos[sq], ori + 9ll * sq);
+				bonds += (v == 1);
+				overlap |= (v == -1);
+			}
+		}
+	}
+	bonds = cg::reduce(tile, bonds, cg::plus<int>());
+	overlap = cg::reduce(tile, overlap, cg::bit_or<int>());
+	if(lane == 0) {
+		if(bonds) atomicAdd(&s_bonds, bonds);
+		if(overlap) atomicOr(&s_overlap, 1);
+	}
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		if(s_bonds) atomicAdd((unsigned long long *) &counters->bonds, (unsigned long long) s_bonds);
+		if(s_overlap) atomicOr(&counters->overlap, 1);
+	}
+}
+
+__global__ void k_zero_bonds(Counters *counters) {
+	counters->bonds = 0;
+	counters->overlap = 0;
+}
+
+int launch_total_bonds(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, Counters *counters, cudaStream_t st) {
+	constexpr int G = 8;
+	k_zero_bonds<<<1, 1, 0, st>>>(counters);
+	const int tiles_per_block = kBondThreads / G;
+	int blocks = (sc.n_cells + tiles_per_block - 1) / tiles_per_block;
+	const int cap = 148 * 16 * 4;
+	if(blocks > cap) blocks = cap;
+	if(blocks < 1) blocks = 1;
+	k_total_bonds<G><<<blocks, kBondThreads, 0, st>>>(sc, cell_start, pos, ori, counters);
+	return 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-particle bonded-neighbour counts (the numbers output_print_bonds writes, output.c:213-268).
+// ---------------------------------------------------------------------------------------------
+template<int G>
+__global__ void __launch_bounds__(kBondThreads) k_bond_counts(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
+		const double4 *__restrict__ pos, const double *__restrict__ ori, const int *__restrict__ pid, int *__restrict__ counts) {
+	constexpr int kTiles = kBondThreads / G;
+	__shared__ Neighbourhood s_nb[kTiles];
+	cg::thread_block block = cg::this_thread_block();
+	cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
+	const int tile_in_block = threadIdx.x / G;
+	const int lane = tile.thread_rank();
+	const int nyz = sc.n_side[1] * sc.n_side[2];
+	for(int cell = blockIdx.x * kTiles + tile_in_block; cell < sc.n_cells; cell += gridDim.x * kTiles) {
+		const int first = cell_start[cell], last = cell_start[cell + 1];
+		if(first == last) continue;
+		const int ix = cell / nyz, iy = (cell - ix * nyz) / sc.n_side[2], iz = cell - ix * nyz - iy * sc.n_side[2];
+		Neighbourhood &nb = s_nb[tile_in_block];
+		tile.sync();
+		const int total = build_neighbourhood<G>(tile, sc, cell_start, ix, iy, iz, nb);
+		for(int sp = first; sp < last; sp++) {
+			const double4 p4 = pos[sp];
+			const Vec3 p = {p4.x, p4.y, p4.z};
+			double mp[9], pp[12];
+#pragma unroll
+			for(int k = 0; k < 9; k++) mp[k] = ori[9ll * sp + k];
+			patches_from(sc.base, mp, pp);
+			int bonds = 0;
+			for(int j = lane; j < total; j += G) {
+				const int sq = neighbour_slot(nb, j);
+				if(sq == sp) continue;
+				bonds += (pair_test(sc, p, pp, pos[sq], ori + 9ll * sq) == 1);
+			}
+			bonds = cg::reduce(tile, bonds, cg::plus<int>());
+			if(lane == 0) counts[pid[sp]] = bonds;
+		}
+	}
+}
+
+int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, cudaStream_t st) {
+	constexpr int G = 8;
+	const int tiles_per_block = kBondThreads / G;
+	int blocks = (sc.n_cells + tiles_per_block - 1) / tiles_per_block;
+	const int cap = 148 * 16 * 4;
+	if(blocks > cap) blocks = cap;
+	if(blocks < 1) blocks = 1;
+	k_bond_counts<G><<<blocks, kBondThreads, 0, st>>>(sc, cell_start, pos, ori, pid, counts);
+	return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: rescale positions (MC.c:474-478, 540-545).  Out of place so that a rejected box move keeps
+// the old coordinates bit for bit (the reference divides back, MC.c:505-508, 567-572).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rescale(int N, const double4 *__restrict__ src, double4 *__restrict__ dst, double fx, double fy, double fz,
+		int divide) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double4 p = src[i];
+	if(divide) { // undo of a rejected move the way the reference does it (MC.c:505-508)
+		p.x = __ddiv_rn(p.x, fx);
+		p.y = __ddiv_rn(p.y, fy);
+		p.z = __ddiv_rn(p.z, fz);
+	}
+	else {
+		p.x = __dmul_rn(p.x, fx);
+		p.y = __dmul_rn(p.y, fy);
+		p.z = __dmul_rn(p.z, fz);
+	}
+	dst[i] = p;
+}
+
+int launch_rescale(int N, const double4 *src, double4 *dst, double fx, double fy, double fz, int divide, cudaStream_t st) {
+	if(N == 0) return 0;
+	k_rescale<<<(N + 255) / 256, 256, 0, st>>>(N, src, dst, fx, fy, fz, divide);
+	return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: MC.c:328-335 for a list of proposals against the frozen configuration.  One tile per
+// proposal.  The old energy is taken around the cell of the current position and the new one
+// around the cell of the proposed position, as MC_energy does (MC.c:277).
+// ---------------------------------------------------------------------------------------------
+template<int G>
+__device__ __forceinline__ void probe_bonds(const cg::thread_block_tile<G> &tile, const SimConst &sc, const int *__restrict__ cell_start,
+		const double4 *__restrict__ pos, const double *__restrict__ ori, Neighbourhood &nb, const Vec3 &p, const double *pp, int self_slot,
+		int &bonds, int &overlap) {
+	int ix, iy, iz;
+	cell_index(sc, p.x, p.y, p.z, ix, iy, iz);
+	tile.sync();
+	const int total = build_neighbourhood<G>(tile, sc, cell_start, ix, iy, iz, nb);
+	int b = 0, o = 0;
+	for(int j = tile.thread_rank(); j < total; j += G) {
+		const int sq = neighbour_slot(nb, j);
+		if(sq == self_slot) continue;
+		const int v = pair_test(sc, p, pp, pos[sq], ori + 9ll * sq);
+		b += (v == 1);
+		o |= (v == -1);
+	}
+	bonds = cg::reduce(tile, b, cg::plus<int>());
+	overlap = cg::reduce(tile, o, cg::bit_or<int>());
+}
+
+template<int G>
+__global__ void __launch_bounds__(kBondThreads) k_proposals(const __grid_constant__ SimConst sc, int n, const ProposalIO io,
+		const int *__restrict__ cell_start, const double4 *__restrict__ pos, const double *__restrict__ ori, const int *__restrict__ slot_of) {
+	constexpr int kTiles = kBondThreads / G;
+	__shared__ Neighbourhood s_nb[kTiles];
+	cg::thread_block block = cg::this_thread_block();
+	cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
+	const int tile_in_block = threadIdx.x / G;
+	Neighbourhood &nb = s_nb[tile_in_block];
+	for(int k = blockIdx.x * kTiles + tile_in_block; k < n; k += gridDim.x * kTiles) {
+		const int sp = slot_of[io.idx[k]];
+		const double4 p4 = pos[sp];
+		const Vec3 p_old = {p4.x, p4.y, p4.z};
+		const Vec3 p_new = {__dadd_rn(p4.x, io.disp[3 * k]), __dadd_rn(p4.y, io.disp[3 * k + 1]), __dadd_rn(p4.z, io.disp[3 * k + 2])};
+		double m[9], pp_old[12], pp_new[12];
+#pragma unroll
+		for(int c = 0; c < 9; c++) m[c] = ori[9ll * sp + c];
+		patches_from(sc.base, m, pp_old);
+#pragma unroll
+		for(int c = 0; c < 9; c++) m[c] = io.orient[9ll * k + c];
+		patches_from(sc.base, m, pp_new);
+
+		int b_old, o_old, b_new, o_new;
+		probe_bonds<G>(tile, sc, cell_start, pos, ori, nb, p_old, pp_old, sp, b_old, o_old);
+		probe_bonds<G>(tile, sc, cell_start, pos, ori, nb, p_new, pp_new, sp, b_new, o_new);
+		if(o_new) b_new = 0; // the reference returns E = 0 at the first overlap (MC.c:296-299)
+		if(tile.thread_rank() == 0) {
+			const int dE = b_old - b_new; // energy = -bonds
+			int acc = 0;
+			if(!o_new) acc = (dE < 0) || (io.u[k] < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]);
+			int a, b, c, a2, b2, c2;
+			const int c_old = cell_index(sc, p_old.x, p_old.y, p_old.z, a, b, c);
+			const int c_new = cell_index(sc, p_new.x, p_new.y, p_new.z, a2, b2, c2);
+			io.dE[k] = dE;
+			io.overlap[k] = o_new;
+			io.accept[k] = acc;
+			io.cell_changed[k] = (c_old != c_new);
+		}
+	}
+}
+
+int launch_proposals(const SimConst &sc, int n, const ProposalIO &io, const int *cell_start, const double4 *pos, const double *ori, const int *slot_of,
+		cudaStream_t st) {
+	if(n == 0) return 0;
+	constexpr int G = 8;
+	const int tiles_per_block = kBondThreads / G;
+	int blocks = (n + tiles_per_block - 1) / tiles_per_block;
+	const int cap = 148 * 16 * 4;
+	if(blocks > cap) blocks = cap;
+	k_proposals<G><<<blocks, kBondThreads, 0, st>>>(sc, n, io, cell_start, pos, ori, slot_of);
+	return 1;
+}
+
+__global__ void k_commit(int slot, const double *__restrict__ disp, const double *__restrict__ orient, double4 *pos, double *ori) {
+	if(threadIdx.x == 0) {
+		double4 p = pos[slot];
+		p.x = __dadd_rn(p.x, disp[0]);
+		p.y = __dadd_rn(p.y, disp[1]);
+		p.z = __dadd_rn(p.z, disp[2]);
+		pos[slot] = p;
+	}
+	if(threadIdx.x < 9) ori[9ll * slot + threadIdx.x] = orient[threadIdx.x];
+}
+
+int launch_commit(int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, cudaStream_t st) {
+	k_commit<<<1, 32, 0, st>>>(slot, disp3, orient9, pos, ori);
+	return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: Gram-Schmidt on the rows of every orientation matrix (utils.c:91-113 as used by
+// MC_check_energy, MC.c:774).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_orthonormalise(int N, double *__restrict__ ori) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	double m[9];
+#pragma unroll
+	for(int k = 0; k < 9; k++) m[k] = ori[9ll * i + k];
+	double *v1 = m, *v2 = m + 3, *v3 = m + 6;
+	const double v1n2 = dot3_rn(v1[0], v1[1], v1[2], v1[0], v1[1], v1[2]);
+	const double b1 = __ddiv_rn(dot3_rn(v2[0], v2[1], v2[2], v1[0], v1[1], v1[2]), v1n2);
+#pragma unroll
+	for(int k = 0; k < 3; k++) v2[k] = __dsub_rn(v2[k], __dmul_rn(b1, v1[k]));
+	const double v3v1 = dot3_rn(v3[0], v3[1], v3[2], v1[0], v1[1], v1[2]);
+	const double v3v2 = dot3_rn(v3[0], v3[1], v3[2], v2[0], v2[1], v2[2]);
+	const double v2n2 = dot3_rn(v2[0], v2[1], v2[2], v2[0], v2[1], v2[2]);
+	const double c1 = __ddiv_rn(v3v1, v1n2), c2 = __ddiv_rn(v3v2, v2n2);
+#pragma unroll
+	for(int k = 0; k < 3; k++) v3[k] = __dsub_rn(v3[k], __dadd_rn(__dmul_rn(c1, v1[k]), __dmul_rn(c2, v2[k])));
+#pragma unroll
+	for(int r = 0; r < 3; r++) {
+		double *v = m + 3 * r;
+		const double n = __dsqrt_rn(dot3_rn(v[0], v[1], v[2], v[0], v[1], v[2]));
+		v[0] = __ddiv_rn(v[0], n);
+		v[1] = __ddiv_rn(v[1], n);
+		v[2] = __ddiv_rn(v[2], n);
+	}
+#pragma unroll
+	for(int k = 0; k < 9; k++) ori[9ll * i + k] = m[k];
+}
+
+int launch_orthonormalise(int N, double *ori, cudaStream_t st) {
+	if(N == 0) return 0;
+	k_orthonormalise<<<(N + 255) / 256, 256, 0, st>>>(N, ori);
+	return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload / download: caller order <-> slot order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_state(int N, const double *__restrict__ r, const double *__restrict__ orient, double4 *__restrict__ pos,
+		double *__restrict__ ori, int *__restrict__ pid) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	pos[i] = make_double4(r[3ll * i], r[3ll * i + 1], r[3ll * i + 2], (double) i);
+	pid[i] = i;
+#pragma unroll
+	for(int k = 0; k < 9; k++) ori[9ll * i + k] = orient[9ll * i + k];
+}
+
+__global__ void __launch_bounds__(256) k_unpack_state(int N, const double4 *__restrict__ pos, const double *__restrict__ ori, const int *__restrict__ pid,
+		double *__restrict__ r, double *__restrict__ orient) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if(s >= N) return;
+	const int i = pid[s];
+	const double4 p = pos[s];
+	r[3ll * i] = p.x;
+	r[3ll * i + 1] = p.y;
+	r[3ll * i + 2] = p.z;
+#pragma unroll
+	for(int k = 0; k < 9; k++) orient[9ll * i + k] = ori[9ll * s + k];
+}
+
+int launch_pack_state(int N, const double *r, const double *orient, double4 *pos, double *ori, int *pid, cudaStream_t st) {
+	if(N == 0) return 0;
+	k_pack_state<<<(N + 255) / 256, 256, 0, st>>>(N, r, orient, pos, ori, pid);
+	return 1;
+}
+
+int launch_unpack_state(int N, const double4 *pos, const double *ori, const int *pid, double *r, double *orient, cudaStream_t st) {
+	if(N == 0) return 0;
+	k_unpack_state<<<(N + 255) / 256, 256, 0, st>>>(N, pos, ori, pid, r, orient);
+	return 1;
+}
+
+} // namespace pp

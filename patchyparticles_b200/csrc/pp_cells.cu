@@ -1,0 +1,162 @@
+// pp_cells.cu -- K1: on-GPU cell build as a counting sort (replaces cells_init + cells_fill,
+// cells.c:17-63, and the incremental relinking of MC_change_cell, MC.c:180-206).
+//
+// count -> exclusive scan -> scatter source indices -> order each cell by particle id -> gather.
+// The result is the particle state permuted into cell order (SoA: double4 position+id, 3x3 FP64
+// orientation, int id) plus the CSR offsets cell_start[n_cells + 1].  Ordering each cell by
+// particle id makes the layout (and therefore every trajectory) independent of atomic ordering.
+#include "pp_kernels.cuh"
+
+namespace pp {
+
+__global__ void __launch_bounds__(256) k_cell_count(const __grid_constant__ SimConst sc, const double4 *__restrict__ pos, int *__restrict__ cell_of,
+		int *__restrict__ cell_count) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= sc.N) return;
+	const double4 p = pos[i];
+	int ix, iy, iz;
+	const int c = cell_index(sc, p.x, p.y, p.z, ix, iy, iz);
+	cell_of[i] = c;
+	atomicAdd(cell_count + c, 1);
+}
+
+// ---- exclusive scan over the cell histogram -------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *smem /* 32 ints */, int &block_total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int incl = v;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o) incl += t;
+	}
+	if(lane == 31) smem[warp] = incl;
+	__syncthreads();
+	if(warp == 0) {
+		int w = (lane < (int) (blockDim.x >> 5)) ? smem[lane] : 0;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			const int t = __shfl_up_sync(0xffffffffu, w, o);
+			if(lane >= o) w += t;
+		}
+		smem[lane] = w;
+	}
+	__syncthreads();
+	const int warp_offset = (warp > 0) ? smem[warp - 1] : 0;
+	block_total = smem[(blockDim.x >> 5) - 1];
+	__syncthreads();
+	return warp_offset + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ tile_sums, int n) {
+	__shared__ int smem[32];
+	const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+	int v[kScanItems], sum = 0;
+#pragma unroll
+	for(int k = 0; k < kScanItems; k++) {
+		v[k] = (base + k < n) ? in[base + k] : 0;
+		sum += v[k];
+	}
+	int total;
+	int run = block_exclusive_scan(sum, smem, total);
+#pragma unroll
+	for(int k = 0; k < kScanItems; k++) {
+		if(base + k < n) out[base + k] = run;
+		run += v[k];
+	}
+	if(threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(int *__restrict__ tile_sums, int n_tiles, int *__restrict__ grand_total) {
+	__shared__ int smem[32];
+	int carry = 0;
+	for(int base = 0; base < n_tiles; base += 1024) {
+		const int i = base + threadIdx.x;
+		const int v = (i < n_tiles) ? tile_sums[i] : 0;
+		int total;
+		const int ex = block_exclusive_scan(v, smem, total);
+		if(i < n_tiles) tile_sums[i] = carry + ex;
+		carry += total;
+	}
+	if(threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(int *__restrict__ out, const int *__restrict__ tile_sums, int n) {
+	const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+	const int add = tile_sums[blockIdx.x];
+#pragma unroll
+	for(int k = 0; k < kScanItems; k++)
+		if(base + k < n) out[base + k] += add;
+}
+
+// ---- scatter / order / gather -----------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cell_scatter(int N, const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+		int *__restrict__ cell_fill, int *__restrict__ perm) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const int c = cell_of[i];
+	perm[cell_start[c] + atomicAdd(cell_fill + c, 1)] = i;
+}
+
+__global__ void __launch_bounds__(256) k_cell_order(int n_cells, const int *__restrict__ cell_start, int *__restrict__ perm, const int *__restrict__ pid_src) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= n_cells) return;
+	const int b = cell_start[c], e = cell_start[c + 1];
+	for(int a = b + 1; a < e; a++) { // insertion sort by particle id; cells hold a handful of particles
+		const int src = perm[a];
+		const int key = pid_src[src];
+		int k = a - 1;
+		while(k >= b && pid_src[perm[k]] > key) {
+			perm[k + 1] = perm[k];
+			k--;
+		}
+		perm[k + 1] = src;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_cell_gather_pos(int N, const int *__restrict__ perm, const double4 *__restrict__ pos_src,
+		const int *__restrict__ pid_src, double4 *__restrict__ pos_dst, int *__restrict__ pid_dst, int *__restrict__ slot_of) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if(s >= N) return;
+	const int src = perm[s];
+	pos_dst[s] = pos_src[src];
+	const int id = pid_src[src];
+	pid_dst[s] = id;
+	slot_of[id] = s;
+}
+
+__global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int *__restrict__ perm, const double *__restrict__ ori_src,
+		double *__restrict__ ori_dst) {
+	const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= n9) return;
+	const int s = (int) (t / 9), comp = (int) (t - 9ll * s);
+	ori_dst[t] = ori_src[9ll * perm[s] + comp];
+}
+
+// ---------------------------------------------------------------------------------------------
+int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, cudaStream_t st) {
+	const int N = sc.N, nc = sc.n_cells;
+	if(N == 0) {
+		cudaMemsetAsync(cb.cell_start, 0, sizeof(int) * (size_t) (nc + 1), st);
+		return 0;
+	}
+	cudaMemsetAsync(cb.cell_count, 0, sizeof(int) * (size_t) nc, st);
+	cudaMemsetAsync(cb.cell_fill, 0, sizeof(int) * (size_t) nc, st);
+	const int nb = (N + 255) / 256;
+	k_cell_count<<<nb, 256, 0, st>>>(sc, src.pos, cb.cell_of, cb.cell_count);
+	const int n_tiles = (nc + kScanTile - 1) / kScanTile;
+	k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_count, cb.cell_start, cb.tile_sums, nc);
+	k_scan_sums<<<1, 1024, 0, st>>>(cb.tile_sums, n_tiles, cb.cell_start + nc);
+	k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_start, cb.tile_sums, nc);
+	k_cell_scatter<<<nb, 256, 0, st>>>(N, cb.cell_of, cb.cell_start, cb.cell_fill, cb.perm);
+	k_cell_order<<<(nc + 255) / 256, 256, 0, st>>>(nc, cb.cell_start, cb.perm, src.pid);
+	k_cell_gather_pos<<<nb, 256, 0, st>>>(N, cb.perm, src.pos, src.pid, dst.pos, dst.pid, slot_of);
+	const long long n9 = 9ll * N;
+	k_cell_gather_ori<<<(unsigned) ((n9 + 255) / 256), 256, 0, st>>>(n9, cb.perm, src.ori, dst.ori);
+	return 8;
+}
+
+} // namespace pp

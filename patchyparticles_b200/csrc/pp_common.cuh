@@ -1,0 +1,223 @@
+// pp_common.cuh -- device-side building blocks shared by all kernels of the engine.
+//
+// Exact FP64 arithmetic: the Kern-Frenkel pair test, the patch construction and the cell index are
+// evaluated with explicitly rounded operations (__dadd_rn / __dmul_rn / __ddiv_rn / __dsqrt_rn) in
+// the reference's operation order, so bond counts and accept/reject decisions are bit-identical to
+// the CPU reference built without FMA contraction (MC.c:232-266, MC.c:225-227, cells.c:43-49).
+// The library is also compiled with -fmad=false.
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+namespace cg = cooperative_groups;
+
+namespace pp {
+
+constexpr int kMaxExp = 32;
+
+// Per-launch constants (passed by value as a __grid_constant__ kernel parameter).
+struct SimConst {
+	double box[3];
+	double shift[3];      // grid origin shift (0 for the reference-parity kernels)
+	double cell_w[3];     // box / n_side
+	int n_side[3];        // even cell grid
+	int n_cells;
+	int N;
+	double sqr_rcut;      // (1 + delta)^2                               system.c:86
+	double cosmax;        // KF_cosmax
+	double base[12];      // 4 body-frame patch directions                system.c:20-31
+	double exp_table[kMaxExp]; // exp(-k / T) from the host's libm        MC.c:332
+	double disp_max, theta_max;
+	uint32_t seed_lo, seed_hi;
+	uint32_t sweep_lo, sweep_hi8; // sweep index low word, (high word << 8)
+};
+
+// Device-resident counters.
+struct Counters {
+	long long tries, accepted, confined, overlapped;
+	unsigned long long w_tries, w_accepted; // fixed point, 2^-24
+	long long dbonds;       // running change of the bond count from sweeps
+	long long pair_checks;
+	long long bonds;        // K3 result
+	int overlap;            // K3 overlap flag
+	int pad;
+};
+
+struct Vec3 {
+	double x, y, z;
+};
+
+// ---------------------------------------------------------------------------------------------
+// exact helpers (no contraction)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dot3_rn(double ax, double ay, double az, double bx, double by, double bz) {
+	// utils.h:15  ((a0*b0 + a1*b1) + a2*b2)
+	return __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+}
+
+// patch[i] = M . base[i]                                                   utils.h:17-21
+__device__ __forceinline__ void patches_from(const double *base, const double *m, double *patches) {
+#pragma unroll
+	for(int i = 0; i < 4; i++) {
+		const double bx = base[3 * i], by = base[3 * i + 1], bz = base[3 * i + 2];
+		patches[3 * i] = dot3_rn(m[0], m[1], m[2], bx, by, bz);
+		patches[3 * i + 1] = dot3_rn(m[3], m[4], m[5], bx, by, bz);
+		patches[3 * i + 2] = dot3_rn(m[6], m[7], m[8], bx, by, bz);
+	}
+}
+
+// cells.c:43-49 with an optional origin shift (shift = 0 reproduces the reference index)
+__device__ __forceinline__ int cell_coord(double r, double shift, double box, int n_side) {
+	double q = __ddiv_rn(__dsub_rn(r, shift), box);
+	double f = __dsub_rn(q, floor(q));
+	return (int) __dmul_rn(__dmul_rn(f, 1. - DBL_EPSILON), (double) n_side);
+}
+
+__device__ __forceinline__ int cell_index(const SimConst &sc, double x, double y, double z, int &ix, int &iy, int &iz) {
+	ix = cell_coord(x, sc.shift[0], sc.box[0], sc.n_side[0]);
+	iy = cell_coord(y, sc.shift[1], sc.box[1], sc.n_side[1]);
+	iz = cell_coord(z, sc.shift[2], sc.box[2], sc.n_side[2]);
+	return (ix * sc.n_side[1] + iy) * sc.n_side[2] + iz;
+}
+
+// Minimum-image separation and its square.                                  MC.c:233-238
+__device__ __forceinline__ double min_image(const SimConst &sc, const Vec3 &p, const double4 &q, Vec3 &d) {
+	d.x = __dsub_rn(q.x, p.x);
+	d.y = __dsub_rn(q.y, p.y);
+	d.z = __dsub_rn(q.z, p.z);
+	d.x = __dsub_rn(d.x, __dmul_rn(sc.box[0], rint(__ddiv_rn(d.x, sc.box[0]))));
+	d.y = __dsub_rn(d.y, __dmul_rn(sc.box[1], rint(__ddiv_rn(d.y, sc.box[1]))));
+	d.z = __dsub_rn(d.z, __dmul_rn(sc.box[2], rint(__ddiv_rn(d.z, sc.box[2]))));
+	return dot3_rn(d.x, d.y, d.z, d.x, d.y, d.z);
+}
+
+// Orientation test for a pair already known to be inside the bonding shell.   MC.c:241-262
+// ori_q points at q's 3x3 matrix in global memory; it is only read if one of p's patches
+// points at q (the reference only enters its inner loop in that case).
+__device__ __forceinline__ bool patches_bond(const SimConst &sc, Vec3 d, double d2, const double *pp, const double *__restrict__ ori_q) {
+	const double norm = __dsqrt_rn(d2);
+	d.x = __ddiv_rn(d.x, norm);
+	d.y = __ddiv_rn(d.y, norm);
+	d.z = __ddiv_rn(d.z, norm);
+	bool p_points = false;
+#pragma unroll
+	for(int i = 0; i < 4; i++) p_points |= (dot3_rn(d.x, d.y, d.z, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]) > sc.cosmax);
+	if(!p_points) return false;
+	double mq[9];
+#pragma unroll
+	for(int k = 0; k < 9; k++) mq[k] = ori_q[k];
+	bool q_points = false;
+#pragma unroll
+	for(int j = 0; j < 4; j++) {
+		const double bx = sc.base[3 * j], by = sc.base[3 * j + 1], bz = sc.base[3 * j + 2];
+		const double qx = dot3_rn(mq[0], mq[1], mq[2], bx, by, bz);
+		const double qy = dot3_rn(mq[3], mq[4], mq[5], bx, by, bz);
+		const double qz = dot3_rn(mq[6], mq[7], mq[8], bx, by, bz);
+		q_points |= (-dot3_rn(d.x, d.y, d.z, qx, qy, qz) > sc.cosmax);
+	}
+	return q_points;
+}
+
+// Full pair test: -1 overlap, 0 none, 1 bond                                 MC.c:232-266
+__device__ __forceinline__ int pair_test(const SimConst &sc, const Vec3 &p, const double *pp, const double4 &q, const double *__restrict__ ori_q) {
+	Vec3 d;
+	const double d2 = min_image(sc, p, q, d);
+	if(d2 < 1.) return -1;
+	if(d2 < sc.sqr_rcut) return patches_bond(sc, d, d2, pp, ori_q) ? 1 : 0;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+	for(int round = 0; round < 10; round++) {
+		const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		const uint32_t n0 = hi1 ^ c1 ^ k0;
+		const uint32_t n2 = hi0 ^ c3 ^ k1;
+		c0 = n0;
+		c1 = lo1;
+		c2 = n2;
+		c3 = lo0;
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+	return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u32_to_unit(uint32_t x) {
+	return __dmul_rn(__dadd_rn((double) x, 0.5), 1.0 / 4294967296.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 27-cell neighbourhood of a home cell as a prefix-summed table in shared memory.
+// An axis with only two cells has offsets {0, +1} (the -1 neighbour is the same cell).
+// ---------------------------------------------------------------------------------------------
+struct Neighbourhood {
+	int first[27]; // first particle slot of neighbour cell l
+	int incl[27];  // inclusive prefix of particle counts
+};
+
+template<int G>
+__device__ __forceinline__ int build_neighbourhood(const cg::thread_block_tile<G> &tile, const SimConst &sc, const int *__restrict__ cell_start,
+		int ix, int iy, int iz, Neighbourhood &nb) {
+	int running = 0;
+	for(int base = 0; base < 27; base += G) {
+		const int l = base + (int) tile.thread_rank();
+		int cnt = 0, first = 0;
+		if(l < 27) {
+			const int dx = l / 9 - 1, dy = (l / 3) % 3 - 1, dz = l % 3 - 1;
+			const bool dup = (sc.n_side[0] == 2 && dx < 0) || (sc.n_side[1] == 2 && dy < 0) || (sc.n_side[2] == 2 && dz < 0);
+			if(!dup) {
+				int cx = ix + dx, cy = iy + dy, cz = iz + dz;
+				cx += (cx < 0) ? sc.n_side[0] : 0;
+				cx -= (cx >= sc.n_side[0]) ? sc.n_side[0] : 0;
+				cy += (cy < 0) ? sc.n_side[1] : 0;
+				cy -= (cy >= sc.n_side[1]) ? sc.n_side[1] : 0;
+				cz += (cz < 0) ? sc.n_side[2] : 0;
+				cz -= (cz >= sc.n_side[2]) ? sc.n_side[2] : 0;
+				const int c = (cx * sc.n_side[1] + cy) * sc.n_side[2] + cz;
+				first = cell_start[c];
+				cnt = cell_start[c + 1] - first;
+			}
+		}
+		int scan = cnt;
+#pragma unroll
+		for(int o = 1; o < G; o <<= 1) {
+			const int v = tile.shfl_up(scan, o);
+			if((int) tile.thread_rank() >= o) scan += v;
+		}
+		if(l < 27) {
+			nb.first[l] = first;
+			nb.incl[l] = running + scan;
+		}
+		running += tile.shfl(scan, G - 1);
+	}
+	tile.sync();
+	return running;
+}
+
+// flat neighbour index j -> particle slot
+__device__ __forceinline__ int neighbour_slot(const Neighbourhood &nb, int j) {
+	int lo = 0, hi = 26; // first l with incl[l] > j
+#pragma unroll
+	for(int it = 0; it < 5; it++) {
+		const int mid = (lo + hi) >> 1;
+		if(nb.incl[mid] > j) hi = mid;
+		else lo = mid + 1;
+	}
+	const int before = (lo > 0) ? nb.incl[lo - 1] : 0;
+	return nb.first[lo] + (j - before);
+}
+
+__device__ __forceinline__ double4 ld_pos(const double4 *__restrict__ pos, int slot) {
+	return pos[slot];
+}
+
+} // namespace pp

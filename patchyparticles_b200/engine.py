@@ -1,0 +1,222 @@
+"""ctypes mirror of include/pp_b200.h (the drop-in C ABI).
+
+Names follow the reference's vocabulary: an :class:`Engine` plays the role of ``System`` plus its
+``do_ensemble`` plugin (defs.h:58-112, MC.c:85-131); ``sweep`` is one or more MC steps
+(main.c:119); ``total_bonds`` is the from-scratch energy of main.c:55-61.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+N_MOVES = 8
+ROTO_TRASL, VOLUME, LX = 0, 6, 7
+NVT, NPT = 0, 5
+K_CELLS, K_SWEEP, K_BONDS, K_RESCALE, K_PROPOSALS, K_ORTHO = range(6)
+KERNEL_CLASSES = ["cells", "sweep", "bonds", "rescale", "proposals", "ortho"]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """pp_params: the input-file keys of the hot path (system.c:61-196)."""
+    _fields_ = [("ensemble", C.c_int), ("temperature", C.c_double), ("disp_max", C.c_double),
+                ("theta_max", C.c_double), ("kf_delta", C.c_double), ("kf_cosmax", C.c_double),
+                ("P", C.c_double), ("rescale_factor_max", C.c_double), ("Lx_move", C.c_int),
+                ("Lx_change_max", C.c_double), ("Lyz_min", C.c_double), ("Lyz_max", C.c_double),
+                ("Lx_reference_sign", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
+                ("lanes_per_cell", C.c_int), ("use_graph", C.c_int)]
+
+
+class Observables(C.Structure):
+    """pp_observables: what output_print reads from System (output.c:119-196)."""
+    _fields_ = [("step", C.c_longlong), ("N", C.c_int), ("box", C.c_double * 3), ("energy", C.c_double),
+                ("tries", C.c_longlong * N_MOVES), ("accepted", C.c_longlong * N_MOVES),
+                ("confined", C.c_longlong), ("overlapped", C.c_longlong), ("acceptance_roto", C.c_double),
+                ("pair_checks", C.c_longlong), ("n_side", C.c_int * 3)]
+
+
+def library_path():
+    return os.path.join(_HERE, "libpatchy_b200.so")
+
+
+_lib = None
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+# every symbol include/pp_b200.h declares
+ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy", "pp_last_error", "pp_upload",
+               "pp_download", "pp_total_bonds", "pp_bond_counts", "pp_sweep", "pp_sync", "pp_get_observables",
+               "pp_check_energy", "pp_eval_proposals", "pp_volume_move", "pp_Lx_move", "pp_set_stream",
+               "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats"]
+
+
+def load_library():
+    """Loads libpatchy_b200.so; raises LibraryMissing if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise LibraryMissing(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "or `make -C patchyparticles_b200/csrc`. There is no CPU fallback.")
+    L = C.CDLL(path)
+    H = C.c_void_p
+    L.pp_default_params.argtypes = [C.POINTER(Params)]
+    L.pp_default_params.restype = None
+    L.pp_create.argtypes = [C.POINTER(Params), C.POINTER(H)]
+    L.pp_destroy.argtypes = [H]
+    L.pp_last_error.argtypes = [H]
+    L.pp_last_error.restype = C.c_char_p
+    L.pp_upload.argtypes = [H, C.c_int, _dp, _dp, _dp]
+    L.pp_download.argtypes = [H, _dp, _dp]
+    L.pp_total_bonds.argtypes = [H, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    L.pp_bond_counts.argtypes = [H, _ip]
+    L.pp_sweep.argtypes = [H, C.c_longlong]
+    L.pp_sync.argtypes = [H]
+    L.pp_get_observables.argtypes = [H, C.POINTER(Observables), C.c_int]
+    L.pp_check_energy.argtypes = [H, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pp_eval_proposals.argtypes = [H, C.c_int, _ip, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
+    L.pp_volume_move.argtypes = [H, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int)]
+    L.pp_Lx_move.argtypes = [H, C.c_double, C.c_double, C.POINTER(C.c_int)]
+    L.pp_set_stream.argtypes = [H, C.c_void_p]
+    L.pp_set_profiling.argtypes = [H, C.c_int]
+    L.pp_kernel_stats.argtypes = [H, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+    L.pp_reset_kernel_stats.argtypes = [H]
+    _lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One GPU's Monte Carlo engine (pp_handle)."""
+
+    def __init__(self, ensemble=NVT, temperature=0.1, disp_max=0.1, theta_max=0.1, kf_delta=0.119, kf_cosmax=0.98,
+                 P=0.0, rescale_factor_max=0.0, Lx_move=0, Lx_change_max=0.0, Lyz_min=0.0, Lyz_max=0.0,
+                 Lx_reference_sign=1, seed=12345, device=0, lanes_per_cell=0, use_graph=0):
+        self.L = load_library()
+        p = Params()
+        self.L.pp_default_params(C.byref(p))
+        p.ensemble, p.temperature, p.disp_max, p.theta_max = ensemble, temperature, disp_max, theta_max
+        p.kf_delta, p.kf_cosmax, p.P, p.rescale_factor_max = kf_delta, kf_cosmax, P, rescale_factor_max
+        p.Lx_move, p.Lx_change_max, p.Lyz_min, p.Lyz_max = Lx_move, Lx_change_max, Lyz_min, Lyz_max
+        p.Lx_reference_sign, p.seed, p.device = Lx_reference_sign, seed, device
+        p.lanes_per_cell, p.use_graph = lanes_per_cell, use_graph
+        self.params = p
+        self.h = C.c_void_p()
+        rc = self.L.pp_create(C.byref(p), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.pp_last_error(self.h).decode() if self.h else "pp_create failed"
+            if self.h:
+                self.L.pp_destroy(self.h)
+            self.h = None
+            raise EngineError(msg)
+        self.N = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.L.pp_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ----------------------------------------------------------------------------
+    def upload(self, box, r, orient):
+        r = np.ascontiguousarray(r, dtype=np.float64).reshape(-1, 3)
+        orient = np.ascontiguousarray(orient, dtype=np.float64).reshape(-1, 9)
+        box = np.ascontiguousarray(box, dtype=np.float64)
+        self.N = int(r.shape[0])
+        if self.N == 0:
+            r, orient = np.zeros((1, 3)), np.zeros((1, 9))
+        self._check(self.L.pp_upload(self.h, self.N, box, r, orient))
+
+    def download(self):
+        r = np.zeros((max(self.N, 1), 3))
+        m = np.zeros((max(self.N, 1), 9))
+        self._check(self.L.pp_download(self.h, r, m))
+        return r[:self.N], m[:self.N].reshape(-1, 3, 3)
+
+    # ---- energies --------------------------------------------------------------------------
+    def total_bonds(self):
+        b, ov = C.c_longlong(0), C.c_int(0)
+        self._check(self.L.pp_total_bonds(self.h, C.byref(b), C.byref(ov)))
+        return int(b.value), int(ov.value)
+
+    def bond_counts(self):
+        c = np.zeros(max(self.N, 1), dtype=np.int32)
+        self._check(self.L.pp_bond_counts(self.h, c))
+        return c[:self.N]
+
+    def check_energy(self):
+        b, ov, ok = C.c_longlong(0), C.c_int(0), C.c_int(0)
+        self._check(self.L.pp_check_energy(self.h, C.byref(b), C.byref(ov), C.byref(ok)))
+        return int(b.value), int(ov.value), bool(ok.value)
+
+    # ---- moves -----------------------------------------------------------------------------
+    def sweep(self, nsteps=1, sync=True):
+        self._check(self.L.pp_sweep(self.h, int(nsteps)))
+        if sync:
+            self._check(self.L.pp_sync(self.h))
+
+    def sync(self):
+        self._check(self.L.pp_sync(self.h))
+
+    def observables(self, reset=False):
+        o = Observables()
+        self._check(self.L.pp_get_observables(self.h, C.byref(o), int(reset)))
+        return o
+
+    def eval_proposals(self, idx, disp, orient_new, u, commit=False):
+        n = len(idx)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        disp = np.ascontiguousarray(disp, dtype=np.float64).reshape(-1, 3)
+        orient_new = np.ascontiguousarray(orient_new, dtype=np.float64).reshape(-1, 9)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        dE = np.zeros(max(n, 1), dtype=np.int32)
+        ov = np.zeros(max(n, 1), dtype=np.int32)
+        acc = np.zeros(max(n, 1), dtype=np.int32)
+        if n:
+            self._check(self.L.pp_eval_proposals(self.h, n, idx, disp, orient_new, u, int(commit), dE, ov, acc))
+        return dE[:n], ov[:n], acc[:n]
+
+    def volume_move(self, u_dir, u_vol, u_acc):
+        a = C.c_int(0)
+        self._check(self.L.pp_volume_move(self.h, u_dir, u_vol, u_acc, C.byref(a)))
+        return int(a.value)
+
+    def Lx_move(self, u_lx, u_acc):
+        a = C.c_int(0)
+        self._check(self.L.pp_Lx_move(self.h, u_lx, u_acc, C.byref(a)))
+        return int(a.value)
+
+    # ---- measurement plumbing --------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._check(self.L.pp_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def set_profiling(self, enable):
+        self._check(self.L.pp_set_profiling(self.h, int(bool(enable))))
+
+    def kernel_stats(self):
+        out = {}
+        for k, name in enumerate(KERNEL_CLASSES):
+            n, ms = C.c_longlong(0), C.c_double(0)
+            self._check(self.L.pp_kernel_stats(self.h, k, C.byref(n), C.byref(ms)))
+            out[name] = (int(n.value), float(ms.value))
+        return out
+
+    def reset_kernel_stats(self):
+        self._check(self.L.pp_reset_kernel_stats(self.h))

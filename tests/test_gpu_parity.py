@@ -1,0 +1,217 @@
+"""GPU parity tests: every call goes through the C ABI (libpatchy_b200.so) and is compared with
+the CPU oracle (oracle/pp_oracle.c, pinned against the unmodified reference) and with the golden
+vectors generated from the reference itself (tools/make_golden.py).
+
+Bar: bit-exact integer bond counts, overlap flags, deltaE and accept/reject decisions (FP64
+threshold tests, MC.c:232-266, 328-335); bit-exact positions; orientations within 4e-15 after
+sweeps (CUDA's sincos and glibc's sin/cos may differ in the last bit).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pp():
+    import patchyparticles_b200 as pkg
+    pkg.load_library()
+    return pkg
+
+
+def make_engine(pp, params, **kw):
+    return pp.Engine(kf_delta=float(params[0]), kf_cosmax=float(params[1]), temperature=float(params[2]), **kw)
+
+
+@pytest.mark.parametrize("name", ["fcc", "bcc", "gen1000_rho0.1", "gen2000_rho0.5"])
+def test_total_bonds_golden(pp, name):
+    g = load_golden(name)
+    for tag in ("a", "b"):
+        if f"energy_{tag}" not in g:
+            continue
+        e = make_engine(pp, g[f"params_{tag}"])
+        e.upload(g["box"], g["r"], g["orient"])
+        bonds, ov = e.total_bonds()
+        assert -bonds == g[f"energy_{tag}"][0]
+        assert ov == g[f"energy_{tag}"][1]
+        assert np.array_equal(e.bond_counts(), g[f"bond_counts_{tag}"])
+        e.close()
+
+
+@pytest.mark.parametrize("name", ["fcc", "bcc", "gen1000_rho0.1", "gen2000_rho0.5"])
+def test_proposals_frozen_golden(pp, name):
+    g = load_golden(name)
+    e = make_engine(pp, g["params_a"])
+    e.upload(g["box"], g["r"], g["orient"])
+    dE, ov, acc = e.eval_proposals(g["prop_idx"], g["prop_disp"], g["prop_orient"], g["prop_u"])
+    assert np.array_equal(ov, g["prop_overlap"])
+    assert np.array_equal(dE, g["prop_dE"])
+    assert np.array_equal(acc, g["prop_accept"])
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["fcc", "gen2000_rho0.5"])
+def test_proposals_sequential_golden(pp, name):
+    g = load_golden(name)
+    n = len(g["seq_dE"])
+    e = make_engine(pp, g["params_a"])
+    e.upload(g["box"], g["r"], g["orient"])
+    e.total_bonds()
+    dE, ov, acc = e.eval_proposals(g["prop_idx"][:n], g["prop_disp"][:n], g["prop_orient"][:n], g["prop_u"][:n], commit=True)
+    assert np.array_equal(ov, g["seq_overlap"])
+    assert np.array_equal(dE, g["seq_dE"])
+    assert np.array_equal(acc, g["seq_accept"])
+    r, m = e.download()
+    assert np.array_equal(r, g["seq_r"])
+    assert np.array_equal(m, g["seq_orient"])
+    assert e.observables().energy == g["seq_energy"][0]
+    bonds, _ = e.total_bonds()
+    assert -bonds == g["seq_energy"][0]
+    e.close()
+
+
+def test_roundtrip_and_edges(pp, oracle):
+    # upload -> download is the identity in the caller's particle order
+    box, r, m = pp.random_fluid(3000, 0.4, seed=3)
+    e = pp.Engine()
+    e.upload(box, r, m)
+    r2, m2 = e.download()
+    assert np.array_equal(r, r2) and np.array_equal(m, m2)
+    # empty system
+    e.upload(box, np.zeros((0, 3)), np.zeros((0, 3, 3)))
+    assert e.total_bonds() == (0, 0)
+    e.sweep(2)
+    # single particle
+    e.upload(box, r[:1], m[:1])
+    assert e.total_bonds() == (0, 0)
+    e.sweep(3)
+    assert e.observables().tries[0] == 3
+    # overlapping pair is flagged
+    rr = r[:2].copy()
+    rr[1] = rr[0] + np.array([0.5, 0.1, 0.0])
+    e.upload(box, rr, m[:2])
+    assert e.total_bonds()[1] == 1
+    # smallest supported box: two cells per side, periodic images handled once
+    small = np.array([2.5, 2.5, 2.5])
+    rs = np.array([[0.1, 0.1, 0.1], [1.2, 0.1, 0.1], [0.1, 1.3, 2.4], [2.45, 1.25, 1.2]])
+    ms = m[:4]
+    e.upload(small, rs, ms)
+    port = oracle.PortSystem(small, rs, ms)
+    assert e.total_bonds() == port.total_bonds()
+    # box too small for the checkerboard is refused with a message
+    with pytest.raises(Exception):
+        e.upload(np.array([2.0, 5.0, 5.0]), rs, ms)
+    e.close()
+
+
+@pytest.mark.parametrize("N,rho,delta,cosmax", [(2000, 0.5, 0.119, 0.98), (1500, 0.3, 0.25, 0.8), (4000, 0.6, 0.119, 0.92)])
+def test_total_bonds_vs_port(pp, oracle, N, rho, delta, cosmax):
+    box, r, m = pp.random_fluid(N, rho, seed=N)
+    box = box * np.array([1.0, 1.1, 1.05])  # anisotropic box (stretching cannot create overlaps)
+    r = r * np.array([1.0, 1.1, 1.05])
+    port = oracle.PortSystem(box, r, m, kf_delta=delta, kf_cosmax=cosmax)
+    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax)
+    e.upload(box, r, m)
+    assert e.total_bonds() == port.total_bonds()
+    assert np.array_equal(e.bond_counts(), port.bond_counts()[0])
+    e.close()
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+def test_sweep_matches_port(pp, oracle, lanes):
+    """The CUDA sweep and the serial restatement of the same algorithm give the same trajectory."""
+    g = load_golden("gen2000_rho0.5")
+    delta, cosmax, T = 0.25, 0.8, 0.15  # plenty of bonds
+    port = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T, disp_max=0.2, theta_max=0.3, seed=99, lanes_per_cell=lanes)
+    e.upload(g["box"], g["r"], g["orient"])
+    bonds, _ = e.total_bonds()
+    pb, _ = port.total_bonds()
+    assert bonds == pb
+    st = oracle.SweepStats()
+    for s in range(6):
+        pb, st = port.sweep(99, s, 0.2, 0.3, pb, st)
+        e.sweep(1)
+        o = e.observables()
+        assert -o.energy == pb, f"sweep {s}"
+        assert o.tries[0] == st.tries and o.accepted[0] == st.accepted
+        assert o.confined == st.confined and o.overlapped == st.overlapped
+        assert o.pair_checks == st.pair_checks
+        assert o.acceptance_roto == st.w_accepted / st.w_tries
+    r, m = e.download()
+    pr, pm = port.state()
+    assert np.array_equal(r, pr)
+    assert np.abs(m - pm).max() < 4e-15
+    b2, ov, ok = e.check_energy()
+    assert ok and b2 == pb and ov == 0
+    e.close()
+
+
+def test_sweep_invariants_large(pp):
+    """MC_check_energy / cells_check equivalents on the bench-size system (N = 65536, rho = 0.5)."""
+    box, r, m = pp.random_fluid(65536, 0.5, seed=11)
+    e = pp.Engine(temperature=0.12, seed=5)
+    e.upload(box, r, m)
+    b0, ov = e.total_bonds()
+    assert ov == 0
+    e.sweep(20)
+    o = e.observables()
+    assert o.tries[0] == 20 * 65536
+    b, ov, ok = e.check_energy()
+    assert ok and ov == 0 and -o.energy == b
+    r2, m2 = e.download()
+    # orientations stay orthonormal, particles moved but not far
+    assert np.abs(np.einsum("nij,nkj->nik", m2, m2) - np.eye(3)).max() < 1e-12
+    assert 0 < np.abs(r2 - r).max() < 20 * 0.05 * 1.01
+    e.close()
+
+
+def test_volume_move_vs_port(pp, oracle):
+    g = load_golden("gen2000_rho0.5")
+    delta, cosmax, T, P, rfm = 0.25, 0.8, 0.15, 0.5, 0.0005
+    port = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    e = pp.Engine(ensemble=5, kf_delta=delta, kf_cosmax=cosmax, temperature=T, P=P, rescale_factor_max=rfm)
+    e.upload(g["box"], g["r"], g["orient"])
+    bonds, _ = e.total_bonds()
+    pb, _ = port.total_bonds()
+    rng = np.random.default_rng(5)
+    n_acc = 0
+    for k in range(40):
+        u = rng.random(3)
+        acc_p, pb, ov = port.volume_move(P, rfm, u[0], u[1], u[2], pb)
+        acc_g = e.volume_move(u[0], u[1], u[2])
+        assert acc_g == acc_p, f"move {k}"
+        o = e.observables()
+        assert -o.energy == pb
+        assert np.array_equal(np.array(o.box), port.box())
+        n_acc += acc_g
+    assert 0 < n_acc < 40
+    r, m = e.download()
+    pr, pm = port.state()
+    assert np.abs(r - pr).max() < 1e-12  # rejected moves: the reference divides back, the engine keeps the old bits
+    assert e.observables().tries[6] == 40 and e.observables().accepted[6] == n_acc
+    e.close()
+
+
+def test_Lx_move_vs_port(pp, oracle):
+    g = load_golden("gen2000_rho0.5")
+    delta, cosmax, T = 0.25, 0.8, 0.15
+    port = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    L = float(g["box"][1])
+    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T, Lx_move=1, Lx_change_max=0.01, Lyz_min=L - 0.002, Lyz_max=L + 0.002)
+    e.upload(g["box"], g["r"], g["orient"])
+    e.total_bonds()
+    pb, _ = port.total_bonds()
+    rng = np.random.default_rng(6)
+    seen = set()
+    for k in range(40):
+        u = rng.random(2)
+        acc_p, pb, ov = port.Lx_move(0.01, L - 0.002, L + 0.002, u[0], u[1], pb)
+        acc_g = e.Lx_move(u[0], u[1])
+        assert acc_g == acc_p, f"move {k}"
+        assert -e.observables().energy == pb
+        seen.add(acc_g)
+    assert seen == {-1, 0, 1}
+    e.close()
