@@ -60,6 +60,7 @@ typedef struct pp_params {
 	int device;                 /* CUDA device ordinal */
 	int lanes_per_cell;         /* sweep-kernel tile width: 0 = default; 4, 8, 16 or 32 */
 	int use_graph;              /* 1: replay the per-sweep launch sequence as a CUDA graph */
+	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
 } pp_params;
 
 typedef struct pp_observables {

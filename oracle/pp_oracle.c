@@ -506,6 +506,7 @@ void ppo_even_grid(const double *box, double r_cut, int *n_side) {
 	for(k = 0; k < 3; k++) {
 		int n = (int) floor(box[k] / r_cut);
 		n &= ~1;
+		if(n >= 2 && box[k] / n < r_cut * (1. + 1e-9)) n -= 2;
 		n_side[k] = n; /* < 2 means the box is too small for the checkerboard */
 	}
 }
@@ -519,26 +520,34 @@ void ppo_sweep_shift(uint64_t seed, uint64_t sweep, const double *box, const int
 	for(k = 0; k < 3; k++) shift[k] = u32_to_unit(x[k]) * (box[k] / n_side[k]);
 }
 
-static int shifted_cell(const double *r, const double *shift, const double *box, const int *n_side, int *idx) {
+/* cell of a position on the sweep's own grid (the engine's cell_coord, pp_common.cuh) */
+static int grid_cell(const double *r, const double *shift, const double *inv_box, const int *n_side, int *idx) {
 	int k;
 	for(k = 0; k < 3; k++) {
-		double f = (r[k] - shift[k]) / box[k];
-		f -= floor(f);
-		idx[k] = (int) (f * (1. - DBL_EPSILON) * n_side[k]);
+		double t = (r[k] - shift[k]) * inv_box[k];
+		double f = t - floor(t);
+		int c = (int) (f * (double) n_side[k]);
+		idx[k] = c < n_side[k] ? c : n_side[k] - 1;
 	}
 	return (idx[0] * n_side[1] + idx[1]) * n_side[2] + idx[2];
 }
 
-void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep, double disp_max, double theta_max, long long *energy_bonds, ppo_sweep_stats *st) {
+void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep, int shift_every, double disp_max, double theta_max, long long *energy_bonds,
+		ppo_sweep_stats *st) {
 	int n_side[3], k, i;
-	double shift[3], w[3];
+	double shift[3], inv_box[3], inv_w[3];
 	ppo_even_grid(s->box, s->r_cut, n_side);
 	if(n_side[0] < 2 || n_side[1] < 2 || n_side[2] < 2) {
 		fprintf(stderr, "ppo_sweep: box too small for the checkerboard\n");
 		abort();
 	}
-	ppo_sweep_shift(seed, sweep, s->box, n_side, shift);
-	for(k = 0; k < 3; k++) w[k] = s->box[k] / n_side[k];
+	/* the shift is redrawn every shift_every sweeps; in between the cell membership cannot change
+	 * (moves are confined), so re-binning every sweep with the period's shift is equivalent */
+	ppo_sweep_shift(seed, sweep / (uint64_t) shift_every, s->box, n_side, shift);
+	for(k = 0; k < 3; k++) {
+		inv_box[k] = 1. / s->box[k];
+		inv_w[k] = (double) n_side[k] * inv_box[k];
+	}
 	int n_cells = n_side[0] * n_side[1] * n_side[2];
 
 	/* counting sort by shifted cell; ascending particle id inside a cell */
@@ -547,7 +556,7 @@ void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep, double disp_max, do
 	int *cell_of = malloc(sizeof(int) * (size_t) s->N);
 	int idx[3];
 	for(i = 0; i < s->N; i++) {
-		cell_of[i] = shifted_cell(s->r + 3 * i, shift, s->box, n_side, idx);
+		cell_of[i] = grid_cell(s->r + 3 * i, shift, inv_box, n_side, idx);
 		start[cell_of[i] + 1]++;
 	}
 	for(i = 0; i < n_cells; i++) start[i + 1] += start[i];
@@ -614,11 +623,11 @@ void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep, double disp_max, do
 						st->tries++;
 
 						double r_new[3] = {s->r[3 * p] + disp[0], s->r[3 * p + 1] + disp[1], s->r[3 * p + 2] + disp[2]};
-						if(shifted_cell(r_new, shift, s->box, n_side, idx) != cell) {
+						if(grid_cell(r_new, shift, inv_box, n_side, idx) != cell) {
 							st->confined++;
 							continue;
 						}
-						double W = 1. / ((1. - fabs(disp[0]) / w[0]) * (1. - fabs(disp[1]) / w[1]) * (1. - fabs(disp[2]) / w[2]));
+						double W = 1. / ((1. - fabs(disp[0]) * inv_w[0]) * (1. - fabs(disp[1]) * inv_w[1]) * (1. - fabs(disp[2]) * inv_w[2]));
 						uint64_t Wfix = (uint64_t) (W * 16777216.0);
 						st->w_tries += Wfix;
 

@@ -84,7 +84,7 @@ typedef struct {
 /* one sweep = 8 colour passes on an even grid of side >= r_cut shifted by shift[3];
  * RNG = Philox4x32-10 keyed by seed, counter (sweep, cell, trial, draw block).
  * Updates s in place; *energy_bonds is the running bond count. */
-void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep_index, double disp_max, double theta_max,
+void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep_index, int shift_every, double disp_max, double theta_max,
 		long long *energy_bonds, ppo_sweep_stats *stats);
 void ppo_even_grid(const double *box, double r_cut, int *n_side);
 void ppo_sweep_shift(uint64_t seed, uint64_t sweep_index, const double *box, const int *n_side, double *shift);

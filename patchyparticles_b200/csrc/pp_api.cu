@@ -77,6 +77,7 @@ struct pp_handle {
 	int n_cells;
 	double shift[3];
 	bool cells_valid;
+	bool sweep_grid; // the current cells were built for the current sweep period's shift
 
 	// bookkeeping
 	long long step;
@@ -122,10 +123,12 @@ void base_patches_host(double *base) {
 }
 
 // even grid with cells of side >= r_cut (cells.c:22-28 uses floor(box / r_cut), any parity)
+// the 1e-9 margin keeps non-adjacent cells more than r_cut apart whatever the rounding of the cell index
 int even_grid(const double *box, double r_cut, int *n_side) {
 	for(int k = 0; k < 3; k++) {
 		int n = (int) floor(box[k] / r_cut);
 		n &= ~1;
+		if(n >= 2 && box[k] / n < r_cut * (1. + 1e-9)) n -= 2;
 		if(n < 2) return 1;
 		n_side[k] = n;
 	}
@@ -198,6 +201,8 @@ SimConst make_const(const pp_handle *h, const double *box, const double *shift) 
 		sc.shift[k] = shift[k];
 		sc.n_side[k] = h->n_side[k];
 		sc.cell_w[k] = box[k] / h->n_side[k];
+		sc.inv_box[k] = 1. / box[k];
+		sc.inv_w[k] = (double) h->n_side[k] * sc.inv_box[k];
 	}
 	sc.n_cells = h->n_cells;
 	sc.N = h->N;
@@ -252,6 +257,7 @@ int rebin(pp_handle *h, const double *shift) {
 	h->cp = np;
 	h->co = no;
 	h->cells_valid = true;
+	h->sweep_grid = false;
 	CUDA_OK(h, cudaGetLastError());
 	return 0;
 }
@@ -322,7 +328,7 @@ int box_trial(pp_handle *h, const double *nb, const double *f, long long *bonds_
 	prof_end(h, PP_K_RESCALE, nl);
 	int ns[3];
 	bool regrid = even_grid(nb, h->r_cut, ns) != 0;
-	for(int k = 0; k < 3 && !regrid; k++) regrid = (nb[k] / h->n_side[k] < h->r_cut * (1. + 1e-12));
+	for(int k = 0; k < 3 && !regrid; k++) regrid = (nb[k] / h->n_side[k] < h->r_cut * (1. + 1e-9));
 	if(regrid) return 2; // caller takes the slow path
 	double sh[3] = {h->shift[0] * f[0], h->shift[1] * f[1], h->shift[2] * f[2]};
 	return count_bonds(h, tp, nb, sh, bonds_new, overlap);
@@ -380,6 +386,7 @@ int volume_move(pp_handle *h, double u_dir, double u_vol, double u_acc, int *acc
 		}
 		h->bonds_base = bonds_new - h->h_counters->dbonds;
 		h->accepted[PP_VOLUME]++;
+		h->sweep_grid = false;
 	}
 	else if(slow) {
 		// go back: divide the coordinates back like the reference and rebuild the cells for the old box
@@ -430,6 +437,7 @@ int Lx_move(pp_handle *h, double u_lx, double u_acc, int *accepted) {
 		}
 		h->bonds_base = bonds_new - h->h_counters->dbonds;
 		h->accepted[PP_LX]++;
+		h->sweep_grid = false;
 	}
 	else if(slow) {
 		const int tp = (h->cp + 2) % 3;
@@ -501,6 +509,7 @@ int pp_create(const pp_params *params, pp_handle **out) {
 	h->r_cut = 1. + params->kf_delta; // system.c:249
 	base_patches_host(h->base);
 	if(h->prm.lanes_per_cell != 4 && h->prm.lanes_per_cell != 8 && h->prm.lanes_per_cell != 16 && h->prm.lanes_per_cell != 32) h->prm.lanes_per_cell = 8;
+	if(h->prm.shift_every < 1) h->prm.shift_every = 4;
 	return 0;
 }
 
@@ -568,6 +577,7 @@ int pp_upload(pp_handle *h, int N, const double *box, const double *r, const dou
 	CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(Counters), h->stream));
 	memset(h->h_counters, 0, sizeof(Counters));
 	h->cells_valid = false;
+	h->sweep_grid = false;
 	h->step = 0;
 	h->bonds_base = 0;
 	h->bonds_known = false;
@@ -641,13 +651,19 @@ int pp_sweep(pp_handle *h, long long nsteps) {
 				if(Lx_move(h, u_lx, u_acc, &acc)) return 1;
 			}
 		}
-		// per-sweep random grid shift in [0, cell width)
-		uint32_t x[4];
-		philox_host(kTagShift, 0u, (uint32_t) h->step, (uint32_t) (((uint64_t) h->step >> 32) << 8), (uint32_t) h->prm.seed, (uint32_t) (h->prm.seed >> 32), x);
-		if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box too small for the checkerboard");
-		double shift[3];
-		for(int k = 0; k < 3; k++) shift[k] = unit_from_u32(x[k]) * (h->box[k] / h->n_side[k]);
-		if(rebin(h, shift)) return 1;
+		// random grid shift in [0, cell width), redrawn every shift_every sweeps; between redraws the cell
+		// lists stay valid because accepted moves never leave their cell
+		const long long period = h->prm.shift_every;
+		if(!h->sweep_grid || !h->cells_valid || h->step % period == 0) {
+			const uint64_t epoch = (uint64_t) (h->step / period);
+			uint32_t x[4];
+			philox_host(kTagShift, 0u, (uint32_t) epoch, (uint32_t) ((epoch >> 32) << 8), (uint32_t) h->prm.seed, (uint32_t) (h->prm.seed >> 32), x);
+			if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box too small for the checkerboard");
+			double shift[3];
+			for(int k = 0; k < 3; k++) shift[k] = unit_from_u32(x[k]) * (h->box[k] / h->n_side[k]);
+			if(rebin(h, shift)) return 1;
+			h->sweep_grid = true;
+		}
 		const SimConst sc = make_const(h, h->box, h->shift);
 		prof_begin(h);
 		int nl = 0;

@@ -24,6 +24,8 @@ struct SimConst {
 	double box[3];
 	double shift[3];      // grid origin shift (0 for the reference-parity kernels)
 	double cell_w[3];     // box / n_side
+	double inv_box[3];    // 1 / box (host-rounded)
+	double inv_w[3];      // n_side * inv_box
 	int n_side[3];        // even cell grid
 	int n_cells;
 	int N;
@@ -70,35 +72,53 @@ __device__ __forceinline__ void patches_from(const double *base, const double *m
 	}
 }
 
-// cells.c:43-49 with an optional origin shift (shift = 0 reproduces the reference index)
-__device__ __forceinline__ int cell_coord(double r, double shift, double box, int n_side) {
-	double q = __ddiv_rn(__dsub_rn(r, shift), box);
-	double f = __dsub_rn(q, floor(q));
-	return (int) __dmul_rn(__dmul_rn(f, 1. - DBL_EPSILON), (double) n_side);
+// Cell of a position on the engine's own (even, shifted) grid.  Any grid with cells of side >= r_cut
+// finds the same pairs as the reference's (cells.c:43-49), so the index itself needs no parity with
+// the reference; it only has to be identical in the cell build, the confinement test and the CPU
+// restatement of the sweep (oracle/pp_oracle.c: grid_cell).
+__device__ __forceinline__ int cell_coord(double r, double shift, double inv_box, int n_side) {
+	const double t = __dmul_rn(__dsub_rn(r, shift), inv_box);
+	const double f = __dsub_rn(t, floor(t));
+	const int c = (int) __dmul_rn(f, (double) n_side);
+	return c < n_side ? c : n_side - 1;
 }
 
 __device__ __forceinline__ int cell_index(const SimConst &sc, double x, double y, double z, int &ix, int &iy, int &iz) {
-	ix = cell_coord(x, sc.shift[0], sc.box[0], sc.n_side[0]);
-	iy = cell_coord(y, sc.shift[1], sc.box[1], sc.n_side[1]);
-	iz = cell_coord(z, sc.shift[2], sc.box[2], sc.n_side[2]);
+	ix = cell_coord(x, sc.shift[0], sc.inv_box[0], sc.n_side[0]);
+	iy = cell_coord(y, sc.shift[1], sc.inv_box[1], sc.n_side[1]);
+	iz = cell_coord(z, sc.shift[2], sc.inv_box[2], sc.n_side[2]);
 	return (ix * sc.n_side[1] + iy) * sc.n_side[2] + iz;
 }
 
-// Minimum-image separation and its square.                                  MC.c:233-238
-__device__ __forceinline__ double min_image(const SimConst &sc, const Vec3 &p, const double4 &q, Vec3 &d) {
-	d.x = __dsub_rn(q.x, p.x);
-	d.y = __dsub_rn(q.y, p.y);
-	d.z = __dsub_rn(q.z, p.z);
-	d.x = __dsub_rn(d.x, __dmul_rn(sc.box[0], rint(__ddiv_rn(d.x, sc.box[0]))));
-	d.y = __dsub_rn(d.y, __dmul_rn(sc.box[1], rint(__ddiv_rn(d.y, sc.box[1]))));
-	d.z = __dsub_rn(d.z, __dmul_rn(sc.box[2], rint(__ddiv_rn(d.z, sc.box[2]))));
-	return dot3_rn(d.x, d.y, d.z, d.x, d.y, d.z);
+// rint(d / box) as the reference computes it (MC.c:234-236), without the division in the common
+// case: rint(d * inv_box) can only differ from rint(d / box) when the quotient is within a couple
+// of ulps of a half-integer, and then the IEEE division is used.
+__device__ __forceinline__ double image_count(double d, double box, double inv_box) {
+	const double q = __dmul_rn(d, inv_box);
+	const double k = rint(q);
+	if(__builtin_expect(0.5 - fabs(__dsub_rn(q, k)) < 1e-7, 0)) return rint(__ddiv_rn(d, box));
+	return k;
 }
 
-// Orientation test for a pair already known to be inside the bonding shell.   MC.c:241-262
+// Minimum-image separation and its square, bit-identical to MC.c:233-238.
+__device__ __forceinline__ double min_image(const SimConst &sc, const Vec3 &p, double qx, double qy, double qz, Vec3 &d) {
+	d.x = __dsub_rn(qx, p.x);
+	d.y = __dsub_rn(qy, p.y);
+	d.z = __dsub_rn(qz, p.z);
+	d.x = __dsub_rn(d.x, __dmul_rn(sc.box[0], image_count(d.x, sc.box[0], sc.inv_box[0])));
+	d.y = __dsub_rn(d.y, __dmul_rn(sc.box[1], image_count(d.y, sc.box[1], sc.inv_box[1])));
+	d.z = __dsub_rn(d.z, __dmul_rn(sc.box[2], image_count(d.z, sc.box[2], sc.inv_box[2])));
+	return dot3_rn(d.x, d.y, d.z, d.x, d.y, d.z);
+}
+__device__ __forceinline__ double min_image(const SimConst &sc, const Vec3 &p, const double4 &q, Vec3 &d) {
+	return min_image(sc, p, q.x, q.y, q.z, d);
+}
+
+// Orientation test for a pair already known to be inside the bonding shell, exactly as MC.c:241-262
+// (normalise by IEEE divisions, left-to-right dot products, strict comparisons).
 // ori_q points at q's 3x3 matrix in global memory; it is only read if one of p's patches
 // points at q (the reference only enters its inner loop in that case).
-__device__ __forceinline__ bool patches_bond(const SimConst &sc, Vec3 d, double d2, const double *pp, const double *__restrict__ ori_q) {
+static __device__ __noinline__ bool patches_bond_exact(const SimConst &sc, Vec3 d, double d2, const double *pp, const double *ori_q) {
 	const double norm = __dsqrt_rn(d2);
 	d.x = __ddiv_rn(d.x, norm);
 	d.y = __ddiv_rn(d.y, norm);
@@ -120,6 +140,39 @@ __device__ __forceinline__ bool patches_bond(const SimConst &sc, Vec3 d, double 
 		q_points |= (-dot3_rn(d.x, d.y, d.z, qx, qy, qz) > sc.cosmax);
 	}
 	return q_points;
+}
+
+// Same decision as patches_bond_exact, computed with one reciprocal square root instead of
+// divisions.  Every cosine is compared with cosmax through a guard band (1e-12, thousands of times
+// the rounding error of the shortcut); a cosine inside the band sends the pair to the exact routine,
+// so the returned decision is always the reference's.
+constexpr double kCosGuard = 1e-12;
+
+__device__ __forceinline__ bool patches_bond(const SimConst &sc, const Vec3 &d, double d2, const double *pp, const double *ori_q) {
+	const double inv = rsqrt(d2);
+	const double hi = __dadd_rn(sc.cosmax, kCosGuard), lo = __dsub_rn(sc.cosmax, kCosGuard);
+	bool pass = false, border = false;
+#pragma unroll
+	for(int i = 0; i < 4; i++) {
+		const double c = __dmul_rn(dot3_rn(d.x, d.y, d.z, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]), inv);
+		pass |= (c > hi);
+		border |= (c >= lo && c <= hi);
+	}
+	if(border) return patches_bond_exact(sc, d, d2, pp, ori_q);
+	if(!pass) return false;
+	// -n . (M_q b_j) = -(M_q^T n) . b_j ; the body-frame patches are (+-1, +-1, +-1) * base[2]  (system.c:23-31)
+	const double vx = dot3_rn(ori_q[0], ori_q[3], ori_q[6], d.x, d.y, d.z);
+	const double vy = dot3_rn(ori_q[1], ori_q[4], ori_q[7], d.x, d.y, d.z);
+	const double vz = dot3_rn(ori_q[2], ori_q[5], ori_q[8], d.x, d.y, d.z);
+	const double s = __dmul_rn(-sc.base[2], inv);
+	const double c0 = __dmul_rn(__dadd_rn(__dsub_rn(-vx, vy), vz), s); // (-1, -1, +1)
+	const double c1 = __dmul_rn(__dsub_rn(__dsub_rn(vx, vy), vz), s);  // (+1, -1, -1)
+	const double c2 = __dmul_rn(__dadd_rn(__dadd_rn(vx, vy), vz), s);  // (+1, +1, +1)
+	const double c3 = __dmul_rn(__dsub_rn(__dsub_rn(vy, vx), vz), s);  // (-1, +1, -1)
+	const double cmax = fmax(fmax(c0, c1), fmax(c2, c3));
+	const bool qborder = (c0 >= lo && c0 <= hi) || (c1 >= lo && c1 <= hi) || (c2 >= lo && c2 <= hi) || (c3 >= lo && c3 <= hi);
+	if(qborder) return patches_bond_exact(sc, d, d2, pp, ori_q);
+	return cmax > hi;
 }
 
 // Full pair test: -1 overlap, 0 none, 1 bond                                 MC.c:232-266

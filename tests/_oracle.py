@@ -73,7 +73,7 @@ def port_lib():
                                   C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.ppo_Lx_move.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                               C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
-    L.ppo_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double,
+    L.ppo_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double,
                             C.POINTER(C.c_longlong), C.POINTER(SweepStats)]
     L.ppo_even_grid.argtypes = [_dp, C.c_double, _ip]
     L.ppo_sweep_shift.argtypes = [C.c_uint64, C.c_uint64, _dp, _ip, _dp]
@@ -192,10 +192,10 @@ class PortSystem:
                                  C.byref(b), C.byref(ov))
         return int(acc), int(b.value), int(ov.value)
 
-    def sweep(self, seed, sweep_index, disp_max, theta_max, bonds, stats=None):
+    def sweep(self, seed, sweep_index, disp_max, theta_max, bonds, stats=None, shift_every=4):
         b = C.c_longlong(bonds)
         st = stats if stats is not None else SweepStats()
-        self.L.ppo_sweep(self.h, seed, sweep_index, disp_max, theta_max, C.byref(b), C.byref(st))
+        self.L.ppo_sweep(self.h, seed, sweep_index, shift_every, disp_max, theta_max, C.byref(b), C.byref(st))
         return int(b.value), st
 
 
