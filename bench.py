@@ -334,6 +334,7 @@ def main():
         "sweep_pass": {"launches": sweep_launches, "ms_per_launch": per_launch_ms, "alg_bytes_per_launch": bytes_per_launch, "GBps": achieved},
         "cell_build": {"launches": stats["cells"][0], "ms_per_build": stats["cells"][1] / n_prof,
                        "GBps": CELLS_BYTES_PER_PARTICLE * N / (stats["cells"][1] / n_prof * 1e-3) / 1e9},
+        "proposals": {"launches": stats["rng"][0], "ms_per_launch": stats["rng"][1] / max(stats["rng"][0], 1)},
         "bond_count": {"launches": stats["bonds"][0], "ms": stats["bonds"][1],
                        "GBps": BONDS_BYTES_PER_PARTICLE * N / (max(stats["bonds"][1], 1e-9) * 1e-3) / 1e9},
     }

@@ -71,6 +71,7 @@ struct pp_handle {
 	Counters *h_counters; // pinned
 	// staging for upload / download / proposals
 	double *d_stage_r, *d_stage_o;
+	Proposal *d_proposals; // one per trial of a sweep
 
 	// grid
 	int n_side[3];
@@ -143,13 +144,18 @@ void free_state(pp_handle *h) {
 	}
 	cudaFree(h->slot_of);
 	cudaFree(h->cb.cell_of);
+	cudaFree(h->cb.cell_sorted);
+	cudaFree(h->cb.posf);
 	cudaFree(h->cb.perm);
+	cudaFree(h->d_proposals);
 	cudaFree(h->d_stage_r);
 	cudaFree(h->d_stage_o);
 	memset(h->pos, 0, sizeof(h->pos));
 	memset(h->ori, 0, sizeof(h->ori));
 	memset(h->pid, 0, sizeof(h->pid));
-	h->slot_of = h->cb.cell_of = h->cb.perm = nullptr;
+	h->slot_of = h->cb.cell_of = h->cb.cell_sorted = h->cb.perm = nullptr;
+	h->d_proposals = nullptr;
+	h->cb.posf = nullptr;
 	h->d_stage_r = h->d_stage_o = nullptr;
 	h->cap_N = 0;
 }
@@ -159,7 +165,8 @@ void free_cells(pp_handle *h) {
 	cudaFree(h->cb.cell_fill);
 	cudaFree(h->cb.cell_start);
 	cudaFree(h->cb.tile_sums);
-	h->cb.cell_count = h->cb.cell_fill = h->cb.cell_start = h->cb.tile_sums = nullptr;
+	cudaFree(h->cb.work);
+	h->cb.cell_count = h->cb.cell_fill = h->cb.cell_start = h->cb.tile_sums = h->cb.work = nullptr;
 	h->cap_cells = 0;
 }
 
@@ -175,6 +182,9 @@ int ensure_state(pp_handle *h, size_t n) {
 	CUDA_OK(h, cudaMalloc(&h->slot_of, cap * sizeof(int)));
 	CUDA_OK(h, cudaMalloc(&h->cb.cell_of, cap * sizeof(int)));
 	CUDA_OK(h, cudaMalloc(&h->cb.perm, cap * sizeof(int)));
+	CUDA_OK(h, cudaMalloc(&h->cb.cell_sorted, cap * sizeof(int)));
+	CUDA_OK(h, cudaMalloc(&h->cb.posf, cap * sizeof(float4)));
+	CUDA_OK(h, cudaMalloc(&h->d_proposals, cap * sizeof(Proposal)));
 	CUDA_OK(h, cudaMalloc(&h->d_stage_r, cap * 3 * sizeof(double)));
 	CUDA_OK(h, cudaMalloc(&h->d_stage_o, cap * 9 * sizeof(double)));
 	h->cap_N = cap;
@@ -189,6 +199,7 @@ int ensure_cells(pp_handle *h, size_t n_cells) {
 	CUDA_OK(h, cudaMalloc(&h->cb.cell_fill, cap * sizeof(int)));
 	CUDA_OK(h, cudaMalloc(&h->cb.cell_start, (cap + 1) * sizeof(int)));
 	CUDA_OK(h, cudaMalloc(&h->cb.tile_sums, (cap / 2048 + 2) * sizeof(int)));
+	CUDA_OK(h, cudaMalloc(&h->cb.work, cap * sizeof(int)));
 	h->cap_cells = cap;
 	return 0;
 }
@@ -208,6 +219,10 @@ SimConst make_const(const pp_handle *h, const double *box, const double *shift) 
 	sc.N = h->N;
 	sc.sqr_rcut = (1. + h->prm.kf_delta) * (1. + h->prm.kf_delta); // system.c:86
 	sc.cosmax = h->prm.kf_cosmax;
+	sc.cos2_lo = sc.cosmax * sc.cosmax * (1. - 1e-11);
+	sc.cos2_hi = sc.cosmax * sc.cosmax * (1. + 1e-11);
+	sc.inv_b2 = 1. / (h->base[2] * h->base[2]);
+	sc.fast_patch = sc.cosmax > 1e-3;
 	memcpy(sc.base, h->base, sizeof(sc.base));
 	for(int k = 0; k < kMaxExp; k++) sc.exp_table[k] = exp(-(double) k / h->prm.temperature); // MC.c:332
 	sc.disp_max = h->prm.disp_max;
@@ -504,11 +519,14 @@ int pp_create(const pp_params *params, pp_handle **out) {
 	CUDA_OK(h, cudaMemset(h->d_counters, 0, sizeof(Counters)));
 	CUDA_OK(h, cudaMallocHost(&h->h_counters, sizeof(Counters)));
 	memset(h->h_counters, 0, sizeof(Counters));
+	CUDA_OK(h, cudaMalloc(&h->cb.bins, sizeof(int) * kBinInts));
+	CUDA_OK(h, cudaMemset(h->cb.bins, 0, sizeof(int) * kBinInts));
 	CUDA_OK(h, cudaEventCreate(&h->ev0));
 	CUDA_OK(h, cudaEventCreate(&h->ev1));
 	h->r_cut = 1. + params->kf_delta; // system.c:249
 	base_patches_host(h->base);
-	if(h->prm.lanes_per_cell != 4 && h->prm.lanes_per_cell != 8 && h->prm.lanes_per_cell != 16 && h->prm.lanes_per_cell != 32) h->prm.lanes_per_cell = 8;
+	if(h->prm.lanes_per_cell != 1 && h->prm.lanes_per_cell != 4 && h->prm.lanes_per_cell != 8 && h->prm.lanes_per_cell != 16 && h->prm.lanes_per_cell != 32)
+		h->prm.lanes_per_cell = 0; // automatic
 	if(h->prm.shift_every < 1) h->prm.shift_every = 4;
 	return 0;
 }
@@ -519,6 +537,7 @@ int pp_destroy(pp_handle *h) {
 	free_state(h);
 	free_cells(h);
 	cudaFree(h->d_counters);
+	cudaFree(h->cb.bins);
 	cudaFreeHost(h->h_counters);
 	if(h->ev0) cudaEventDestroy(h->ev0);
 	if(h->ev1) cudaEventDestroy(h->ev1);
@@ -666,9 +685,18 @@ int pp_sweep(pp_handle *h, long long nsteps) {
 		}
 		const SimConst sc = make_const(h, h->box, h->shift);
 		prof_begin(h);
+		const int nr = launch_proposals_for_sweep(sc, h->cb, h->d_proposals, h->stream);
+		prof_end(h, PP_K_RNG, nr);
+		prof_begin(h);
 		int nl = 0;
-		for(int colour = 0; colour < 8; colour++)
-			nl += launch_sweep_pass(sc, colour, h->prm.lanes_per_cell, h->cb.cell_start, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
+		// lanes_per_cell: 1 = one thread per cell (throughput, large N), 4..32 = one tile per cell (latency, small N)
+		int lanes = h->prm.lanes_per_cell;
+		if(lanes == 0) lanes = (h->N >= 400000) ? 8 : 16; // measured on B200: profiles/README.md
+		if(lanes == 1 && (h->n_side[0] < 4 || h->n_side[1] < 4 || h->n_side[2] < 4)) lanes = 8;
+		for(int colour = 0; colour < 8; colour++) {
+			if(lanes == 1) nl += launch_sweep_cells(sc, colour, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
+			else nl += launch_sweep_pass(sc, colour, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
+		}
 		prof_end(h, PP_K_SWEEP, nl);
 		h->step++;
 	}

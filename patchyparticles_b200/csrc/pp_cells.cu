@@ -5,6 +5,10 @@
 // The result is the particle state permuted into cell order (SoA: double4 position+id, 3x3 FP64
 // orientation, int id) plus the CSR offsets cell_start[n_cells + 1].  Ordering each cell by
 // particle id makes the layout (and therefore every trajectory) independent of atomic ordering.
+//
+// The build also emits the sweep's work lists: for each of the 8 checkerboard colours the non-empty
+// cells, bucketed by occupancy in descending order.  Tiles that share a warp in the sweep kernel
+// then run the same number of trials (no idle tiles), and the longest chains start first.
 #include "pp_kernels.cuh"
 
 namespace pp {
@@ -101,11 +105,23 @@ __global__ void __launch_bounds__(256) k_cell_scatter(int N, const int *__restri
 	perm[cell_start[c] + atomicAdd(cell_fill + c, 1)] = i;
 }
 
-__global__ void __launch_bounds__(256) k_cell_order(int n_cells, const int *__restrict__ cell_start, int *__restrict__ perm, const int *__restrict__ pid_src) {
+// bin of a non-empty cell in the work lists: colour-major, occupancy descending inside a colour
+__device__ __forceinline__ int work_bin(const SimConst &sc, int c, int n) {
+	const int nyz = sc.n_side[1] * sc.n_side[2];
+	const int ix = c / nyz, iy = (c - ix * nyz) / sc.n_side[2], iz = c - ix * nyz - iy * sc.n_side[2];
+	const int colour = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
+	const int bucket = n < kWorkBuckets ? n : kWorkBuckets;        // 1 .. kWorkBuckets
+	return colour * kWorkBuckets + (kWorkBuckets - bucket);           // big cells first
+}
+
+// per cell: order its particles by id (insertion sort; a handful of particles) and count its work bin
+__global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start, int *__restrict__ perm,
+		const int *__restrict__ pid_src, int *__restrict__ bin_count) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= n_cells) return;
+	if(c >= sc.n_cells) return;
 	const int b = cell_start[c], e = cell_start[c + 1];
-	for(int a = b + 1; a < e; a++) { // insertion sort by particle id; cells hold a handful of particles
+	if(e == b) return;
+	for(int a = b + 1; a < e; a++) {
 		const int src = perm[a];
 		const int key = pid_src[src];
 		int k = a - 1;
@@ -115,17 +131,48 @@ __global__ void __launch_bounds__(256) k_cell_order(int n_cells, const int *__re
 		}
 		perm[k + 1] = src;
 	}
+	atomicAdd(bin_count + work_bin(sc, c, e - b), 1);
 }
 
-__global__ void __launch_bounds__(256) k_cell_gather_pos(int N, const int *__restrict__ perm, const double4 *__restrict__ pos_src,
-		const int *__restrict__ pid_src, double4 *__restrict__ pos_dst, int *__restrict__ pid_dst, int *__restrict__ slot_of) {
+// one warp: exclusive scan of the 8 * kWorkBuckets bins; work_start[colour] marks the colour boundaries
+__global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__ bin_start, int *__restrict__ work_start) {
+	__shared__ int s[8 * kWorkBuckets + 1];
+	if(threadIdx.x == 0) {
+		int run = 0;
+		for(int b = 0; b < 8 * kWorkBuckets; b++) {
+			s[b] = run;
+			run += bin_count[b];
+		}
+		s[8 * kWorkBuckets] = run;
+	}
+	__syncthreads();
+	for(int b = threadIdx.x; b <= 8 * kWorkBuckets; b += blockDim.x) bin_start[b] = s[b];
+	if(threadIdx.x <= 8) work_start[threadIdx.x] = s[threadIdx.x * kWorkBuckets];
+}
+
+__global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
+		const int *__restrict__ bin_start, int *__restrict__ bin_fill, int *__restrict__ work) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= sc.n_cells) return;
+	const int n = cell_start[c + 1] - cell_start[c];
+	if(n == 0) return;
+	const int bin = work_bin(sc, c, n);
+	work[bin_start[bin] + atomicAdd(bin_fill + bin, 1)] = c;
+}
+
+__global__ void __launch_bounds__(256) k_cell_gather_pos(const __grid_constant__ SimConst sc, const int *__restrict__ perm,
+		const int *__restrict__ cell_of, const double4 *__restrict__ pos_src, const int *__restrict__ pid_src, double4 *__restrict__ pos_dst,
+		int *__restrict__ pid_dst, int *__restrict__ slot_of, int *__restrict__ cell_sorted, float4 *__restrict__ posf) {
 	const int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if(s >= N) return;
+	if(s >= sc.N) return;
 	const int src = perm[s];
-	pos_dst[s] = pos_src[src];
+	const double4 p = pos_src[src];
+	pos_dst[s] = p;
 	const int id = pid_src[src];
 	pid_dst[s] = id;
 	slot_of[id] = s;
+	cell_sorted[s] = cell_of[src];
+	posf[s] = cell_relative(sc, p.x, p.y, p.z); // FP32 shadow used by the sweep's distance pre-screen
 }
 
 __global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int *__restrict__ perm, const double *__restrict__ ori_src,
@@ -139,24 +186,27 @@ __global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int
 // ---------------------------------------------------------------------------------------------
 int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, cudaStream_t st) {
 	const int N = sc.N, nc = sc.n_cells;
+	cudaMemsetAsync(cb.bins, 0, sizeof(int) * kBinInts, st);
 	if(N == 0) {
 		cudaMemsetAsync(cb.cell_start, 0, sizeof(int) * (size_t) (nc + 1), st);
 		return 0;
 	}
 	cudaMemsetAsync(cb.cell_count, 0, sizeof(int) * (size_t) nc, st);
 	cudaMemsetAsync(cb.cell_fill, 0, sizeof(int) * (size_t) nc, st);
-	const int nb = (N + 255) / 256;
+	const int nb = (N + 255) / 256, ncb = (nc + 255) / 256;
 	k_cell_count<<<nb, 256, 0, st>>>(sc, src.pos, cb.cell_of, cb.cell_count);
 	const int n_tiles = (nc + kScanTile - 1) / kScanTile;
 	k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_count, cb.cell_start, cb.tile_sums, nc);
 	k_scan_sums<<<1, 1024, 0, st>>>(cb.tile_sums, n_tiles, cb.cell_start + nc);
 	k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_start, cb.tile_sums, nc);
 	k_cell_scatter<<<nb, 256, 0, st>>>(N, cb.cell_of, cb.cell_start, cb.cell_fill, cb.perm);
-	k_cell_order<<<(nc + 255) / 256, 256, 0, st>>>(nc, cb.cell_start, cb.perm, src.pid);
-	k_cell_gather_pos<<<nb, 256, 0, st>>>(N, cb.perm, src.pos, src.pid, dst.pos, dst.pid, slot_of);
+	k_cell_order<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.perm, src.pid, cb.bins + kBinCount);
+	k_bins_scan<<<1, 160, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkStart);
+	k_work_scatter<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.bins + kBinStart, cb.bins + kBinFill, cb.work);
+	k_cell_gather_pos<<<nb, 256, 0, st>>>(sc, cb.perm, cb.cell_of, src.pos, src.pid, dst.pos, dst.pid, slot_of, cb.cell_sorted, cb.posf);
 	const long long n9 = 9ll * N;
 	k_cell_gather_ori<<<(unsigned) ((n9 + 255) / 256), 256, 0, st>>>(n9, cb.perm, src.ori, dst.ori);
-	return 8;
+	return 10;
 }
 
 } // namespace pp

@@ -31,6 +31,10 @@ struct SimConst {
 	int N;
 	double sqr_rcut;      // (1 + delta)^2                               system.c:86
 	double cosmax;        // KF_cosmax
+	double cos2_lo, cos2_hi; // cosmax^2 (1 -+ 1e-11): guard band of the division-free patch test
+	double inv_b2;        // 1 / base[2]^2
+	int fast_patch;       // the division-free patch test is valid (cosmax > 0)
+	int pad0;
 	double base[12];      // 4 body-frame patch directions                system.c:20-31
 	double exp_table[kMaxExp]; // exp(-k / T) from the host's libm        MC.c:332
 	double disp_max, theta_max;
@@ -90,6 +94,35 @@ __device__ __forceinline__ int cell_index(const SimConst &sc, double x, double y
 	return (ix * sc.n_side[1] + iy) * sc.n_side[2] + iz;
 }
 
+// FP32 shadow of a position: offset inside its cell along x, y, z and the cell's z index.  Only the
+// sweep's distance pre-screen reads it (with a 1e-3 safety band); every decision is taken in FP64.
+__device__ __forceinline__ float4 cell_relative(const SimConst &sc, double x, double y, double z) {
+	float4 out;
+	{
+		const double t = __dmul_rn(__dsub_rn(x, sc.shift[0]), sc.inv_box[0]);
+		const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) sc.n_side[0]);
+		int c = (int) g;
+		c = c < sc.n_side[0] ? c : sc.n_side[0] - 1;
+		out.x = (float) ((g - (double) c) * sc.cell_w[0]);
+	}
+	{
+		const double t = __dmul_rn(__dsub_rn(y, sc.shift[1]), sc.inv_box[1]);
+		const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) sc.n_side[1]);
+		int c = (int) g;
+		c = c < sc.n_side[1] ? c : sc.n_side[1] - 1;
+		out.y = (float) ((g - (double) c) * sc.cell_w[1]);
+	}
+	{
+		const double t = __dmul_rn(__dsub_rn(z, sc.shift[2]), sc.inv_box[2]);
+		const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) sc.n_side[2]);
+		int c = (int) g;
+		c = c < sc.n_side[2] ? c : sc.n_side[2] - 1;
+		out.z = (float) ((g - (double) c) * sc.cell_w[2]);
+		out.w = (float) c;
+	}
+	return out;
+}
+
 // rint(d / box) as the reference computes it (MC.c:234-236), without the division in the common
 // case: rint(d * inv_box) can only differ from rint(d / box) when the quotient is within a couple
 // of ulps of a half-integer, and then the IEEE division is used.
@@ -118,6 +151,7 @@ __device__ __forceinline__ double min_image(const SimConst &sc, const Vec3 &p, c
 // (normalise by IEEE divisions, left-to-right dot products, strict comparisons).
 // ori_q points at q's 3x3 matrix in global memory; it is only read if one of p's patches
 // points at q (the reference only enters its inner loop in that case).
+template<int S = 1>
 static __device__ __noinline__ bool patches_bond_exact(const SimConst &sc, Vec3 d, double d2, const double *pp, const double *ori_q) {
 	const double norm = __dsqrt_rn(d2);
 	d.x = __ddiv_rn(d.x, norm);
@@ -125,7 +159,7 @@ static __device__ __noinline__ bool patches_bond_exact(const SimConst &sc, Vec3 
 	d.z = __ddiv_rn(d.z, norm);
 	bool p_points = false;
 #pragma unroll
-	for(int i = 0; i < 4; i++) p_points |= (dot3_rn(d.x, d.y, d.z, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]) > sc.cosmax);
+	for(int i = 0; i < 4; i++) p_points |= (dot3_rn(d.x, d.y, d.z, pp[(3 * i) * S], pp[(3 * i + 1) * S], pp[(3 * i + 2) * S]) > sc.cosmax);
 	if(!p_points) return false;
 	double mq[9];
 #pragma unroll
@@ -142,37 +176,78 @@ static __device__ __noinline__ bool patches_bond_exact(const SimConst &sc, Vec3 
 	return q_points;
 }
 
-// Same decision as patches_bond_exact, computed with one reciprocal square root instead of
-// divisions.  Every cosine is compared with cosmax through a guard band (1e-12, thousands of times
-// the rounding error of the shortcut); a cosine inside the band sends the pair to the exact routine,
-// so the returned decision is always the reference's.
-constexpr double kCosGuard = 1e-12;
-
+// Same decision as patches_bond_exact without square root or division: for cosmax > 0,
+//     (d . patch) / |d| > cosmax   <=>   d . patch > 0  and  (d . patch)^2 > cosmax^2 d^2.
+// The squared cosine is compared through a relative guard band of 1e-11 (cos2_lo / cos2_hi, ten
+// thousand times the rounding error of the shortcut); a value inside the band sends the pair to
+// the exact routine, so the returned decision is always the reference's.
+template<int S = 1>
 __device__ __forceinline__ bool patches_bond(const SimConst &sc, const Vec3 &d, double d2, const double *pp, const double *ori_q) {
-	const double inv = rsqrt(d2);
-	const double hi = __dadd_rn(sc.cosmax, kCosGuard), lo = __dsub_rn(sc.cosmax, kCosGuard);
+	if(!sc.fast_patch) return patches_bond_exact<S>(sc, d, d2, pp, ori_q);
+	const double lo = __dmul_rn(sc.cos2_lo, d2), hi = __dmul_rn(sc.cos2_hi, d2);
 	bool pass = false, border = false;
 #pragma unroll
 	for(int i = 0; i < 4; i++) {
-		const double c = __dmul_rn(dot3_rn(d.x, d.y, d.z, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]), inv);
-		pass |= (c > hi);
-		border |= (c >= lo && c <= hi);
+		const double s = dot3_rn(d.x, d.y, d.z, pp[(3 * i) * S], pp[(3 * i + 1) * S], pp[(3 * i + 2) * S]);
+		const double s2 = __dmul_rn(s, s);
+		pass |= (s > 0. && s2 > hi);
+		border |= (s > 0. && s2 >= lo && s2 <= hi);
 	}
-	if(border) return patches_bond_exact(sc, d, d2, pp, ori_q);
+	if(border) return patches_bond_exact<S>(sc, d, d2, pp, ori_q);
 	if(!pass) return false;
 	// -n . (M_q b_j) = -(M_q^T n) . b_j ; the body-frame patches are (+-1, +-1, +-1) * base[2]  (system.c:23-31)
 	const double vx = dot3_rn(ori_q[0], ori_q[3], ori_q[6], d.x, d.y, d.z);
 	const double vy = dot3_rn(ori_q[1], ori_q[4], ori_q[7], d.x, d.y, d.z);
 	const double vz = dot3_rn(ori_q[2], ori_q[5], ori_q[8], d.x, d.y, d.z);
-	const double s = __dmul_rn(-sc.base[2], inv);
-	const double c0 = __dmul_rn(__dadd_rn(__dsub_rn(-vx, vy), vz), s); // (-1, -1, +1)
-	const double c1 = __dmul_rn(__dsub_rn(__dsub_rn(vx, vy), vz), s);  // (+1, -1, -1)
-	const double c2 = __dmul_rn(__dadd_rn(__dadd_rn(vx, vy), vz), s);  // (+1, +1, +1)
-	const double c3 = __dmul_rn(__dsub_rn(__dsub_rn(vy, vx), vz), s);  // (-1, +1, -1)
-	const double cmax = fmax(fmax(c0, c1), fmax(c2, c3));
-	const bool qborder = (c0 >= lo && c0 <= hi) || (c1 >= lo && c1 <= hi) || (c2 >= lo && c2 <= hi) || (c3 >= lo && c3 <= hi);
-	if(qborder) return patches_bond_exact(sc, d, d2, pp, ori_q);
-	return cmax > hi;
+	const double w0 = __dsub_rn(__dadd_rn(vx, vy), vz); // -(-1, -1, +1) . v
+	const double w1 = __dsub_rn(__dadd_rn(vy, vz), vx); // -(+1, -1, -1) . v
+	const double w2 = -__dadd_rn(__dadd_rn(vx, vy), vz); // -(+1, +1, +1) . v
+	const double w3 = __dsub_rn(__dadd_rn(vx, vz), vy); // -(-1, +1, -1) . v
+	const double wmax = fmax(fmax(w0, w1), fmax(w2, w3));
+	if(!(wmax > 0.)) return false;
+	const double lo_q = __dmul_rn(lo, sc.inv_b2), hi_q = __dmul_rn(hi, sc.inv_b2); // thresholds for w^2 (cos = base[2] w / |d|)
+	const double t0 = __dmul_rn(w0, w0), t1 = __dmul_rn(w1, w1), t2 = __dmul_rn(w2, w2), t3 = __dmul_rn(w3, w3);
+	const bool qpass = (w0 > 0. && t0 > hi_q) || (w1 > 0. && t1 > hi_q) || (w2 > 0. && t2 > hi_q) || (w3 > 0. && t3 > hi_q);
+	const bool qborder = (w0 > 0. && t0 >= lo_q && t0 <= hi_q) || (w1 > 0. && t1 >= lo_q && t1 <= hi_q) || (w2 > 0. && t2 >= lo_q && t2 <= hi_q) ||
+			(w3 > 0. && t3 >= lo_q && t3 <= hi_q);
+	if(qborder) return patches_bond_exact<S>(sc, d, d2, pp, ori_q);
+	return qpass;
+}
+
+// The same test when the moved particle's patches have not been formed: d . (M b_i) = (M^T d) . b_i,
+// so its side of the test needs only the 3x3 matrix mp (registers).  Guarded like patches_bond; the
+// exact routine rebuilds the patch vectors with the reference's arithmetic when it is needed.
+__device__ __forceinline__ bool patches_bond_m(const SimConst &sc, const Vec3 &d, double d2, const double *mp, const double *ori_q) {
+	if(sc.fast_patch) {
+		const double lo = __dmul_rn(__dmul_rn(sc.cos2_lo, d2), sc.inv_b2), hi = __dmul_rn(__dmul_rn(sc.cos2_hi, d2), sc.inv_b2);
+		const double ux = dot3_rn(mp[0], mp[3], mp[6], d.x, d.y, d.z);
+		const double uy = dot3_rn(mp[1], mp[4], mp[7], d.x, d.y, d.z);
+		const double uz = dot3_rn(mp[2], mp[5], mp[8], d.x, d.y, d.z);
+		const double p0 = __dsub_rn(uz, __dadd_rn(ux, uy));  // (-1, -1, +1) . u
+		const double p1 = __dsub_rn(ux, __dadd_rn(uy, uz));  // (+1, -1, -1) . u
+		const double p2 = __dadd_rn(__dadd_rn(ux, uy), uz);  // (+1, +1, +1) . u
+		const double p3 = __dsub_rn(uy, __dadd_rn(ux, uz));  // (-1, +1, -1) . u
+		const double s0 = __dmul_rn(p0, p0), s1 = __dmul_rn(p1, p1), s2 = __dmul_rn(p2, p2), s3 = __dmul_rn(p3, p3);
+		const bool ppass = (p0 > 0. && s0 > hi) || (p1 > 0. && s1 > hi) || (p2 > 0. && s2 > hi) || (p3 > 0. && s3 > hi);
+		const bool pborder = (p0 > 0. && s0 >= lo && s0 <= hi) || (p1 > 0. && s1 >= lo && s1 <= hi) || (p2 > 0. && s2 >= lo && s2 <= hi) ||
+				(p3 > 0. && s3 >= lo && s3 <= hi);
+		if(!pborder) {
+			if(!ppass) return false;
+			const double vx = dot3_rn(ori_q[0], ori_q[3], ori_q[6], d.x, d.y, d.z);
+			const double vy = dot3_rn(ori_q[1], ori_q[4], ori_q[7], d.x, d.y, d.z);
+			const double vz = dot3_rn(ori_q[2], ori_q[5], ori_q[8], d.x, d.y, d.z);
+			const double w0 = __dsub_rn(__dadd_rn(vx, vy), vz), w1 = __dsub_rn(__dadd_rn(vy, vz), vx);
+			const double w2 = -__dadd_rn(__dadd_rn(vx, vy), vz), w3 = __dsub_rn(__dadd_rn(vx, vz), vy);
+			const double t0 = __dmul_rn(w0, w0), t1 = __dmul_rn(w1, w1), t2 = __dmul_rn(w2, w2), t3 = __dmul_rn(w3, w3);
+			const bool qpass = (w0 > 0. && t0 > hi) || (w1 > 0. && t1 > hi) || (w2 > 0. && t2 > hi) || (w3 > 0. && t3 > hi);
+			const bool qborder = (w0 > 0. && t0 >= lo && t0 <= hi) || (w1 > 0. && t1 >= lo && t1 <= hi) || (w2 > 0. && t2 >= lo && t2 <= hi) ||
+					(w3 > 0. && t3 >= lo && t3 <= hi);
+			if(!qborder) return qpass;
+		}
+	}
+	double pp[12];
+	patches_from(sc.base, mp, pp);
+	return patches_bond_exact<1>(sc, d, d2, pp, ori_q);
 }
 
 // Full pair test: -1 overlap, 0 none, 1 bond                                 MC.c:232-266

@@ -12,13 +12,35 @@ struct StateView {
 	int *pid;     // particle id per slot
 };
 
+// work lists of the sweep: 8 colours x kWorkBuckets occupancy buckets (descending occupancy)
+constexpr int kWorkBuckets = 16;
+constexpr int kBinCount = 0;                              // [8 * kWorkBuckets] cells per bin
+constexpr int kBinStart = 8 * kWorkBuckets;               // [8 * kWorkBuckets + 1] exclusive prefix
+constexpr int kBinFill = kBinStart + 8 * kWorkBuckets + 1; // [8 * kWorkBuckets] scatter cursors
+constexpr int kWorkStart = kBinFill + 8 * kWorkBuckets;   // [9] first work item of each colour
+constexpr int kBinInts = kWorkStart + 16;
+
 struct CellBuffers {
-	int *cell_of;    // N
-	int *cell_count; // n_cells
-	int *cell_fill;  // n_cells
-	int *cell_start; // n_cells + 1
-	int *tile_sums;  // scan scratch
-	int *perm;       // N
+	int *cell_of;     // N: cell of each particle in source order
+	int *cell_sorted; // N: cell of each slot after the sort
+	int *cell_count;  // n_cells
+	int *cell_fill;   // n_cells
+	int *cell_start;  // n_cells + 1
+	int *tile_sums;   // scan scratch
+	int *perm;        // N
+	int *work;        // n_cells: non-empty cells grouped by colour, occupancy descending
+	int *bins;        // kBinInts
+	float4 *posf;     // N: position inside its cell (x, y, z) and the cell's z index, FP32 (pre-screen only)
+};
+
+// A pre-generated roto-translation proposal (MC.c:312-324): rotation matrix R (new = old . R),
+// displacement, Metropolis uniform and the rank of the picked particle inside its cell.
+struct Proposal {
+	double R[9];
+	double dx, dy, dz;
+	double u_acc;
+	int pick;
+	int pad;
 };
 
 // one proposal of the K5 evaluator (device layout)
@@ -33,8 +55,15 @@ struct ProposalIO {
 // K1: returns the number of kernels launched
 int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, cudaStream_t st);
 
-// K2: one colour pass of the checkerboard sweep
-int launch_sweep_pass(const SimConst &sc, int colour, int lanes, const int *cell_start, double4 *pos, double *ori, Counters *counters, cudaStream_t st);
+// K2a: proposals of all N trials of one sweep (trial t of a cell lives at index cell_start[cell] + t)
+int launch_proposals_for_sweep(const SimConst &sc, const CellBuffers &cb, Proposal *proposals, cudaStream_t st);
+// K2b: one colour pass of the checkerboard sweep
+int launch_sweep_pass(const SimConst &sc, int colour, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
+		Counters *counters, cudaStream_t st);
+
+// K2b, throughput variant: one thread per cell (needs at least 4 cells per axis)
+int launch_sweep_cells(const SimConst &sc, int colour, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori, Counters *counters,
+		cudaStream_t st);
 
 // K3: full bond count + overlap flag into counters->bonds / counters->overlap (zeroed by the launcher)
 int launch_total_bonds(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, Counters *counters, cudaStream_t st);

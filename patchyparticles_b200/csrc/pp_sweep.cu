@@ -1,4 +1,4 @@
-// pp_sweep.cu -- K2: one colour pass of the 8-colour checkerboard sweep.
+// pp_sweep.cu -- K2: the 8-colour checkerboard sweep.
 //
 // Replaces the inner loop of do_NVT / do_NPT (MC.c:19-29, 60-68) together with
 // MC_move_rototranslate, MC_energy, MC_would_interact, MC_rototraslate_particle and
@@ -11,16 +11,21 @@
 // evaluated.  An active cell holding n particles makes n trials, each on a member drawn uniformly
 // with replacement, so a sweep is exactly N attempts like a reference step.
 //
-// One tile of G lanes per active cell:
-//   1. the (deduplicated) 27-cell neighbourhood is staged once in shared memory (positions + slots);
-//   2. the proposals of up to G trials are generated in parallel, one per lane (Philox4x32-10 keyed
-//      by the seed, counter (cell, trial, sweep, block); Marsaglia axis; Rodrigues matrix) and
-//      parked in shared memory;
-//   3. the trials run in order: the lanes share the 3x3 products and the patch vectors of the moved
-//      particle (one element per lane, parked in shared memory), split the staged neighbours,
-//      evaluate the old and new pair state in FP64 with the reference's operation order, reduce
-//      bond counts / overlap across the tile, apply the Metropolis rule and write the accepted
-//      state back to HBM and to the staged copy.
+// Two kernels:
+//   k_make_proposals  one thread per trial of the whole sweep: Philox4x32-10 keyed by the seed,
+//                     counter (cell, trial, sweep, block) -> picked member, displacement, Marsaglia
+//                     axis, Rodrigues matrix, Metropolis uniform (MC.c:312-324).  Fully parallel,
+//                     off the critical path of the passes.
+//   k_sweep_pass      one tile of G lanes per non-empty cell of the current colour, taken from
+//                     the work list (cells bucketed by occupancy, so the tiles of a warp run the
+//                     same number of trials).  The (deduplicated) 27-cell neighbourhood is staged
+//                     once in shared memory; every trial then (1) shares the 3x3 product and the
+//                     patch vectors of the moved particle across the lanes, (2) lets the lanes
+//                     split the staged neighbours for the FP64 distance tests of the old and the
+//                     new position, compacting the pairs inside the bonding shell into a candidate
+//                     list, (3) runs the orientation tests on the candidates, (4) reduces bond
+//                     counts / overlap across the tile, applies the Metropolis rule and writes the
+//                     accepted state back to HBM and to the staged copy.
 // A trajectory depends only on (seed, sweep, cell, trial): not on G, the block size, or the GPU.
 #include "pp_kernels.cuh"
 
@@ -28,41 +33,29 @@ namespace pp {
 
 constexpr int kStageCap = 64; // staged neighbours per cell; denser neighbourhoods read HBM/L2 directly
 
-struct BlockCounters {
-	unsigned long long tries, accepted, confined, overlapped, w_tries, w_accepted, pair_checks;
-	long long dbonds;
-};
-
-struct Proposal {
-	double R[9];
-	double dx, dy, dz;
-	double u_acc;
-	int pick;
-	int pad;
-};
-
-template<int G>
-struct TileSmem {
-	Neighbourhood nb;
-	double x[kStageCap], y[kStageCap], z[kStageCap];
-	int slot[kStageCap];
-	double m_old[9], m_new[9], pp_old[12], pp_new[12];
-	Proposal prop[G];
-};
-
-// proposal of trial t of a cell (MC.c:312-324, utils.c:115-131, 186-202); every number is a pure
-// function of (seed, sweep, cell, t)
-__device__ __forceinline__ void make_proposal(const SimConst &sc, int cell, int t, int n_here, Proposal &pr) {
+// ---------------------------------------------------------------------------------------------
+// K2a: proposals
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
+		const int *__restrict__ cell_sorted, Proposal *__restrict__ out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= sc.N) return;
+	const int cell = cell_sorted[i];
+	const int first = cell_start[cell];
+	const int n_here = cell_start[cell + 1] - first;
+	const int t = i - first;
 	const uint4 x = philox4x32((uint32_t) cell, (uint32_t) t, sc.sweep_lo, sc.sweep_hi8 | 0u, sc.seed_lo, sc.seed_hi);
 	const uint4 y = philox4x32((uint32_t) cell, (uint32_t) t, sc.sweep_lo, sc.sweep_hi8 | 1u, sc.seed_lo, sc.seed_hi);
+	Proposal pr;
 	pr.pick = (int) __umulhi(x.x, (uint32_t) n_here);
+	pr.pad = 0;
 	pr.dx = __dmul_rn(__dsub_rn(u32_to_unit(x.y), 0.5), sc.disp_max);
 	pr.dy = __dmul_rn(__dsub_rn(u32_to_unit(x.z), 0.5), sc.disp_max);
 	pr.dz = __dmul_rn(__dsub_rn(u32_to_unit(x.w), 0.5), sc.disp_max);
 	const double theta = __dmul_rn(u32_to_unit(y.x), sc.theta_max);
 	pr.u_acc = __dmul_rn((double) ((((unsigned long long) y.y) << 21) | (((unsigned long long) y.z) >> 11)), 1.0 / 9007199254740992.0);
 	double ran1, ran2, ransq;
-	for(uint32_t blk = 2;; blk++) { // Marsaglia pairs
+	for(uint32_t blk = 2;; blk++) { // Marsaglia pairs (utils.c:120-124)
 		const uint4 z = philox4x32((uint32_t) cell, (uint32_t) t, sc.sweep_lo, sc.sweep_hi8 | blk, sc.seed_lo, sc.seed_hi);
 		ran1 = __dsub_rn(1., __dmul_rn(2., u32_to_unit(z.x)));
 		ran2 = __dsub_rn(1., __dmul_rn(2., u32_to_unit(z.y)));
@@ -73,6 +66,7 @@ __device__ __forceinline__ void make_proposal(const SimConst &sc, int cell, int 
 		ransq = __dadd_rn(__dmul_rn(ran1, ran1), __dmul_rn(ran2, ran2));
 		if(ransq < 1.) break;
 	}
+	// axis (utils.c:127-131), Rodrigues matrix (utils.c:186-202)
 	const double ranh = __dmul_rn(2., __dsqrt_rn(__dsub_rn(1., ransq)));
 	const double ex = __dmul_rn(ran1, ranh), ey = __dmul_rn(ran2, ranh), ez = __dsub_rn(1., __dmul_rn(2., ransq));
 	double st, ct;
@@ -90,7 +84,33 @@ __device__ __forceinline__ void make_proposal(const SimConst &sc, int cell, int 
 	pr.R[6] = __dsub_rn(xz, ys);
 	pr.R[7] = __dadd_rn(yz, xs);
 	pr.R[8] = __dadd_rn(zz, __dmul_rn(__dsub_rn(1., zz), ct));
+	out[i] = pr;
 }
+
+int launch_proposals_for_sweep(const SimConst &sc, const CellBuffers &cb, Proposal *proposals, cudaStream_t st) {
+	if(sc.N == 0) return 0;
+	k_make_proposals<<<(sc.N + 127) / 128, 128, 0, st>>>(sc, cb.cell_start, cb.cell_sorted, proposals);
+	return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b: colour pass
+// ---------------------------------------------------------------------------------------------
+struct BlockCounters {
+	unsigned int tries, accepted, confined, overlapped;
+	int dbonds;
+	unsigned long long w_tries, w_accepted, pair_checks;
+};
+
+template<int G>
+struct TileSmem {
+	Neighbourhood nb;
+	double x[kStageCap], y[kStageCap], z[kStageCap];
+	int slot[kStageCap];
+	double prop[14]; // R[9], dx, dy, dz, u_acc, (pick, pad)
+	double m_old[9], m_new[9], pp_old[12], pp_new[12];
+	unsigned short cand[2 * kStageCap]; // staged index | (new ? 0x8000 : 0)
+};
 
 // weight of a non-confined trial in the acceptance estimator: 1 / P(this displacement stays in a cell)
 __device__ __forceinline__ unsigned long long trial_weight(const SimConst &sc, double dx, double dy, double dz) {
@@ -105,8 +125,9 @@ __host__ __device__ constexpr int sweep_threads() {
 }
 
 template<int G>
-__global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) k_sweep_pass(const __grid_constant__ SimConst sc, int colour, const int *__restrict__ cell_start,
-		double4 *pos, double *ori, Counters *__restrict__ counters) {
+__global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) k_sweep_pass(const __grid_constant__ SimConst sc, int colour,
+		const int *__restrict__ cell_start, const int *__restrict__ work, const int *__restrict__ work_start, const Proposal *__restrict__ proposals,
+		double4 *pos, double *ori, float4 *posf, Counters *__restrict__ counters) {
 	constexpr int kThreads = sweep_threads<G>();
 	constexpr int kTiles = kThreads / G;
 	__shared__ TileSmem<G> s_tile[kTiles];
@@ -118,21 +139,18 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 	if(threadIdx.x == 0) s_cnt = BlockCounters{0, 0, 0, 0, 0, 0, 0, 0};
 	__syncthreads();
 
-	const int ox = colour & 1, oy = (colour >> 1) & 1, oz = (colour >> 2) & 1;
-	const int hx = sc.n_side[0] >> 1, hy = sc.n_side[1] >> 1, hz = sc.n_side[2] >> 1;
-	const int n_active = hx * hy * hz;
+	const int w_begin = work_start[colour], w_end = work_start[colour + 1];
+	const int nyz = sc.n_side[1] * sc.n_side[2];
 	// per-tile tallies (kept by every lane, flushed by lane 0)
 	unsigned int a_tries = 0, a_acc = 0, a_conf = 0, a_ovl = 0;
 	unsigned long long a_wt = 0, a_wa = 0, a_checks = 0;
 	int a_dbonds = 0;
 
-	for(int a = blockIdx.x * kTiles + (int) (threadIdx.x / G); a < n_active; a += gridDim.x * kTiles) {
-		const int ax = a / (hy * hz), ay = (a - ax * hy * hz) / hz, az = a - ax * hy * hz - ay * hz;
-		const int ix = 2 * ax + ox, iy = 2 * ay + oy, iz = 2 * az + oz;
-		const int cell = (ix * sc.n_side[1] + iy) * sc.n_side[2] + iz;
+	for(int wi = w_begin + blockIdx.x * kTiles + (int) (threadIdx.x / G); wi < w_end; wi += gridDim.x * kTiles) {
+		const int cell = work[wi];
+		const int ix = cell / nyz, iy = (cell - ix * nyz) / sc.n_side[2], iz = cell - ix * nyz - iy * sc.n_side[2];
 		const int first = cell_start[cell];
 		const int n_here = cell_start[cell + 1] - first;
-		if(n_here == 0) continue;
 		tile.sync();
 		const int total = build_neighbourhood<G>(tile, sc, cell_start, ix, iy, iz, ts.nb);
 		const bool staged = total <= kStageCap;
@@ -148,157 +166,203 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 		}
 		const int home_base = ts.nb.incl[12]; // the home cell is entry 13 of the 27-cell table
 
-		for(int t0 = 0; t0 < n_here; t0 += G) {
+		for(int t = 0; t < n_here; t++) {
 			tile.sync();
-			if(t0 + lane < n_here) make_proposal(sc, cell, t0 + lane, n_here, ts.prop[lane]);
+			{ // fetch the proposal of this trial (112 contiguous bytes)
+				const double *src = reinterpret_cast<const double *>(proposals + first + t);
+				for(int k = lane; k < 14; k += G) ts.prop[k] = src[k];
+			}
 			tile.sync();
-			const int n_batch = min(G, n_here - t0);
-			for(int tt = 0; tt < n_batch; tt++) {
-				const Proposal &pr = ts.prop[tt];
-				a_tries++;
-				const int sp = first + pr.pick;
-				const int j_self = home_base + pr.pick;
-				Vec3 p_old;
-				if(staged) p_old = {ts.x[j_self], ts.y[j_self], ts.z[j_self]};
-				else {
-					const double4 p4 = pos[sp];
-					p_old = {p4.x, p4.y, p4.z};
-				}
-				const Vec3 p_new = {__dadd_rn(p_old.x, pr.dx), __dadd_rn(p_old.y, pr.dy), __dadd_rn(p_old.z, pr.dz)};
-				int cx, cy, cz;
-				if(cell_index(sc, p_new.x, p_new.y, p_new.z, cx, cy, cz) != cell) { // would leave its cell
-					a_conf++;
-					continue;
-				}
-				const unsigned long long Wfix = trial_weight(sc, pr.dx, pr.dy, pr.dz);
-				a_wt += Wfix;
+			const double *R = ts.prop;
+			const double dx = ts.prop[9], dy = ts.prop[10], dz = ts.prop[11], u_acc = ts.prop[12];
+			const int pick = reinterpret_cast<const int *>(ts.prop + 13)[0];
+			a_tries++;
+			const int sp = first + pick;
+			const int j_self = home_base + pick;
+			Vec3 p_old;
+			if(staged) p_old = {ts.x[j_self], ts.y[j_self], ts.z[j_self]};
+			else {
+				const double4 p4 = pos[sp];
+				p_old = {p4.x, p4.y, p4.z};
+			}
+			const Vec3 p_new = {__dadd_rn(p_old.x, dx), __dadd_rn(p_old.y, dy), __dadd_rn(p_old.z, dz)};
+			int cx, cy, cz;
+			if(cell_index(sc, p_new.x, p_new.y, p_new.z, cx, cy, cz) != cell) { // would leave its cell
+				a_conf++;
+				continue;
+			}
+			const unsigned long long Wfix = trial_weight(sc, dx, dy, dz);
+			a_wt += Wfix;
 
-				// ---- new orientation and both sets of patches, one element per lane -----------
-				for(int k = lane; k < 9; k += G) ts.m_old[k] = ori[9ll * sp + k];
-				tile.sync();
-				for(int k = lane; k < 9; k += G) {
-					const int i = k / 3, j = k - 3 * i; // new = old . R (utils.c:172-184)
-					ts.m_new[k] = dot3_rn(ts.m_old[3 * i], ts.m_old[3 * i + 1], ts.m_old[3 * i + 2], pr.R[j], pr.R[3 + j], pr.R[6 + j]);
-				}
-				tile.sync();
-				for(int k = lane; k < 24; k += G) { // patch[i][c] = M[c][:] . base[i][:]  (MC.c:225-227)
-					const int kk = k < 12 ? k : k - 12;
-					const int i = kk / 3, c = kk - 3 * i;
-					const double *m = k < 12 ? ts.m_old : ts.m_new;
-					const double v = dot3_rn(m[3 * c], m[3 * c + 1], m[3 * c + 2], sc.base[3 * i], sc.base[3 * i + 1], sc.base[3 * i + 2]);
-					if(k < 12) ts.pp_old[kk] = v;
-					else ts.pp_new[kk] = v;
-				}
-				tile.sync();
-
-				// ---- old / new pair state over the neighbourhood (MC.c:328-330) -------------
-				int b_old = 0, b_new = 0, o_new = 0;
-				for(int j = lane; j < total; j += G) {
-					int sq;
+			// ---- distance tests of the old and new position (MC.c:233-241) --------------------
+			for(int k = lane; k < 9; k += G) ts.m_old[k] = ori[9ll * sp + k]; // in flight during the distance tests
+			int o_new = 0, n_cand = 0;
+			for(int j0 = 0; j0 < total; j0 += G) {
+				const int j = j0 + lane;
+				bool in_old = false, in_new = false;
+				if(j < total) {
+					int sq = 0;
 					double qx, qy, qz;
+					bool self;
 					if(staged) {
-						if(j == j_self) continue;
-						sq = ts.slot[j];
+						self = (j == j_self);
 						qx = ts.x[j];
 						qy = ts.y[j];
 						qz = ts.z[j];
 					}
 					else {
 						sq = neighbour_slot(ts.nb, j);
-						if(sq == sp) continue;
+						self = (sq == sp);
 						const double4 q4 = pos[sq];
 						qx = q4.x;
 						qy = q4.y;
 						qz = q4.z;
 					}
+					if(!self) {
+						Vec3 d;
+						const double d2_old = min_image(sc, p_old, qx, qy, qz, d);
+						const double d2_new = min_image(sc, p_new, qx, qy, qz, d);
+						if(d2_new < 1.) o_new = 1;
+						in_old = (d2_old >= 1. && d2_old < sc.sqr_rcut);
+						in_new = (d2_new >= 1. && d2_new < sc.sqr_rcut);
+					}
+				}
+				if(staged) { // compact the in-shell pairs into the candidate list
+					const unsigned m_old_ = tile.ballot(in_old), m_new_ = tile.ballot(in_new);
+					const unsigned below = (1u << lane) - 1u;
+					if(in_old) ts.cand[n_cand + __popc(m_old_ & below)] = (unsigned short) j;
+					n_cand += __popc(m_old_);
+					if(in_new) ts.cand[n_cand + __popc(m_new_ & below)] = (unsigned short) (j | 0x8000);
+					n_cand += __popc(m_new_);
+				}
+			}
+			a_checks += 2ull * (unsigned long long) (total - 1);
+			if(tile.any(o_new)) { // hard-core overlap: rejected whatever the bonds (MC.c:296-299, 332)
+				a_ovl++;
+				continue;
+			}
+
+			// ---- new orientation and both sets of patches, one element per lane -----------
+			tile.sync();
+			for(int k = lane; k < 9; k += G) {
+				const int i = k / 3, j = k - 3 * i; // new = old . R (utils.c:172-184)
+				ts.m_new[k] = dot3_rn(ts.m_old[3 * i], ts.m_old[3 * i + 1], ts.m_old[3 * i + 2], R[j], R[3 + j], R[6 + j]);
+			}
+			tile.sync();
+			for(int k = lane; k < 24; k += G) { // patch[i][c] = M[c][:] . base[i][:]  (MC.c:225-227)
+				const int kk = k < 12 ? k : k - 12;
+				const int i = kk / 3, c = kk - 3 * i;
+				const double *m = k < 12 ? ts.m_old : ts.m_new;
+				const double v = dot3_rn(m[3 * c], m[3 * c + 1], m[3 * c + 2], sc.base[3 * i], sc.base[3 * i + 1], sc.base[3 * i + 2]);
+				if(k < 12) ts.pp_old[kk] = v;
+				else ts.pp_new[kk] = v;
+			}
+			tile.sync();
+
+			// ---- orientation tests on the pairs inside the bonding shell (MC.c:241-262) ---------
+			int b_old = 0, b_new = 0;
+			if(staged) {
+				for(int c = lane; c < n_cand; c += G) {
+					const unsigned e = ts.cand[c];
+					const int j = (int) (e & 0x7fffu);
+					const bool is_new = (e & 0x8000u) != 0;
+					Vec3 d;
+					const double d2 = min_image(sc, is_new ? p_new : p_old, ts.x[j], ts.y[j], ts.z[j], d);
+					const bool bond = patches_bond(sc, d, d2, is_new ? ts.pp_new : ts.pp_old, ori + 9ll * ts.slot[j]);
+					b_old += (bond && !is_new);
+					b_new += (bond && is_new);
+				}
+			}
+			else {
+				for(int j = lane; j < total; j += G) {
+					const int sq = neighbour_slot(ts.nb, j);
+					if(sq == sp) continue;
+					const double4 q4 = pos[sq];
 					Vec3 d_old, d_new;
-					const double d2_old = min_image(sc, p_old, qx, qy, qz, d_old);
-					const double d2_new = min_image(sc, p_new, qx, qy, qz, d_new);
-					if(d2_new < 1.) o_new = 1;
+					const double d2_old = min_image(sc, p_old, q4.x, q4.y, q4.z, d_old);
+					const double d2_new = min_image(sc, p_new, q4.x, q4.y, q4.z, d_new);
 					if(d2_old >= 1. && d2_old < sc.sqr_rcut) b_old += patches_bond(sc, d_old, d2_old, ts.pp_old, ori + 9ll * sq) ? 1 : 0;
 					if(d2_new >= 1. && d2_new < sc.sqr_rcut) b_new += patches_bond(sc, d_new, d2_new, ts.pp_new, ori + 9ll * sq) ? 1 : 0;
 				}
-				a_checks += 2ull * (unsigned long long) (total - 1);
-				// one packed reduction: bonds old | bonds new | overlap
-				const unsigned packed = cg::reduce(tile, (unsigned) b_old | ((unsigned) b_new << 10) | ((unsigned) o_new << 20), cg::plus<unsigned>());
-				b_old = (int) (packed & 1023u);
-				b_new = (int) ((packed >> 10) & 1023u);
-				o_new = (int) (packed >> 20);
+			}
+			const unsigned packed = cg::reduce(tile, (unsigned) b_old | ((unsigned) b_new << 16), cg::plus<unsigned>());
+			b_old = (int) (packed & 0xffffu);
+			b_new = (int) (packed >> 16);
 
-				// ---- Metropolis (MC.c:332-339) ------------------------------------------------
-				if(o_new) {
-					a_ovl++;
-					continue;
-				}
-				const int dE = b_old - b_new; // energy = -bonds
-				if(dE < 0 || pr.u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
-					if(lane == 0) {
-						double *p = reinterpret_cast<double *>(pos + sp); // x, y, z; the id in .w stays
-						p[0] = p_new.x;
-						p[1] = p_new.y;
-						p[2] = p_new.z;
-						if(staged) {
-							ts.x[j_self] = p_new.x;
-							ts.y[j_self] = p_new.y;
-							ts.z[j_self] = p_new.z;
-						}
+			// ---- Metropolis (MC.c:332-339) ------------------------------------------------------
+			const int dE = b_old - b_new; // energy = -bonds
+			if(dE < 0 || u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
+				if(lane == 0) {
+					double *p = reinterpret_cast<double *>(pos + sp); // x, y, z; the id in .w stays
+					p[0] = p_new.x;
+					p[1] = p_new.y;
+					p[2] = p_new.z;
+					posf[sp] = cell_relative(sc, p_new.x, p_new.y, p_new.z);
+					if(staged) {
+						ts.x[j_self] = p_new.x;
+						ts.y[j_self] = p_new.y;
+						ts.z[j_self] = p_new.z;
 					}
-					for(int k = lane; k < 9; k += G) ori[9ll * sp + k] = ts.m_new[k];
-					a_dbonds += b_new - b_old;
-					a_acc++;
-					a_wa += Wfix;
-					tile.sync(); // make the new state visible to the tile's next trial
 				}
+				for(int k = lane; k < 9; k += G) ori[9ll * sp + k] = ts.m_new[k];
+				a_dbonds += b_new - b_old;
+				a_acc++;
+				a_wa += Wfix;
 			}
 		}
 	}
 
 	if(lane == 0 && a_tries) {
-		atomicAdd(&s_cnt.tries, (unsigned long long) a_tries);
-		atomicAdd(&s_cnt.accepted, (unsigned long long) a_acc);
-		atomicAdd(&s_cnt.confined, (unsigned long long) a_conf);
-		atomicAdd(&s_cnt.overlapped, (unsigned long long) a_ovl);
+		atomicAdd(&s_cnt.tries, a_tries);
+		atomicAdd(&s_cnt.accepted, a_acc);
+		atomicAdd(&s_cnt.confined, a_conf);
+		atomicAdd(&s_cnt.overlapped, a_ovl);
+		atomicAdd(&s_cnt.dbonds, a_dbonds);
 		atomicAdd(&s_cnt.w_tries, a_wt);
 		atomicAdd(&s_cnt.w_accepted, a_wa);
 		atomicAdd(&s_cnt.pair_checks, a_checks);
-		atomicAdd((unsigned long long *) &s_cnt.dbonds, (unsigned long long) (long long) a_dbonds);
 	}
 	__syncthreads();
 	if(threadIdx.x == 0 && s_cnt.tries) {
-		atomicAdd((unsigned long long *) &counters->tries, s_cnt.tries);
-		atomicAdd((unsigned long long *) &counters->accepted, s_cnt.accepted);
-		atomicAdd((unsigned long long *) &counters->confined, s_cnt.confined);
-		atomicAdd((unsigned long long *) &counters->overlapped, s_cnt.overlapped);
+		atomicAdd((unsigned long long *) &counters->tries, (unsigned long long) s_cnt.tries);
+		atomicAdd((unsigned long long *) &counters->accepted, (unsigned long long) s_cnt.accepted);
+		atomicAdd((unsigned long long *) &counters->confined, (unsigned long long) s_cnt.confined);
+		atomicAdd((unsigned long long *) &counters->overlapped, (unsigned long long) s_cnt.overlapped);
 		atomicAdd(&counters->w_tries, s_cnt.w_tries);
 		atomicAdd(&counters->w_accepted, s_cnt.w_accepted);
 		atomicAdd((unsigned long long *) &counters->pair_checks, s_cnt.pair_checks);
-		atomicAdd((unsigned long long *) &counters->dbonds, (unsigned long long) s_cnt.dbonds);
+		atomicAdd((unsigned long long *) &counters->dbonds, (unsigned long long) (long long) s_cnt.dbonds);
 	}
 }
 
 template<int G>
-static int launch_pass_g(const SimConst &sc, int colour, const int *cell_start, double4 *pos, double *ori, Counters *counters, cudaStream_t st) {
+static int launch_pass_g(const SimConst &sc, int colour, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori, Counters *counters,
+		cudaStream_t st) {
 	constexpr int kThreads = sweep_threads<G>();
-	const int n_active = (sc.n_side[0] / 2) * (sc.n_side[1] / 2) * (sc.n_side[2] / 2);
+	// the number of non-empty cells of this colour lives on the device (work_start); size the grid for
+	// the worst case (every active cell occupied, at most one cell per particle) and let surplus tiles exit
+	long long n_active = (long long) (sc.n_side[0] / 2) * (sc.n_side[1] / 2) * (sc.n_side[2] / 2);
+	if(n_active > sc.N) n_active = sc.N;
 	const int tiles_per_block = kThreads / G;
-	int blocks = (n_active + tiles_per_block - 1) / tiles_per_block;
-	const int cap = 148 * 32 * 8;
+	long long blocks = (n_active + tiles_per_block - 1) / tiles_per_block;
+	const long long cap = 148ll * 32 * 16;
 	if(blocks > cap) blocks = cap;
 	if(blocks < 1) blocks = 1;
-	k_sweep_pass<G><<<blocks, kThreads, 0, st>>>(sc, colour, cell_start, pos, ori, counters);
+	k_sweep_pass<G><<<(unsigned) blocks, kThreads, 0, st>>>(sc, colour, cb.cell_start, cb.work, cb.bins + kWorkStart, proposals, pos, ori, cb.posf, counters);
 	return 1;
 }
 
-int launch_sweep_pass(const SimConst &sc, int colour, int lanes, const int *cell_start, double4 *pos, double *ori, Counters *counters, cudaStream_t st) {
+int launch_sweep_pass(const SimConst &sc, int colour, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
+		Counters *counters, cudaStream_t st) {
 	switch(lanes) {
 	case 4:
-		return launch_pass_g<4>(sc, colour, cell_start, pos, ori, counters, st);
+		return launch_pass_g<4>(sc, colour, cb, proposals, pos, ori, counters, st);
 	case 8:
-		return launch_pass_g<8>(sc, colour, cell_start, pos, ori, counters, st);
+		return launch_pass_g<8>(sc, colour, cb, proposals, pos, ori, counters, st);
 	case 16:
-		return launch_pass_g<16>(sc, colour, cell_start, pos, ori, counters, st);
+		return launch_pass_g<16>(sc, colour, cb, proposals, pos, ori, counters, st);
 	default:
-		return launch_pass_g<32>(sc, colour, cell_start, pos, ori, counters, st);
+		return launch_pass_g<32>(sc, colour, cb, proposals, pos, ori, counters, st);
 	}
 }
 

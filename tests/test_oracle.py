@@ -1,0 +1,191 @@
+"""CPU tests (no GPU): the oracle restatement against the golden vectors generated from the
+unmodified reference, against the reference library itself when it has been built
+(oracle/_ref/libppref.so), the host-side helpers, and the C-ABI surface of the product library."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+GOLDEN_SETS = ["fcc", "bcc", "gen1000_rho0.1", "gen2000_rho0.5"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_port_total_bonds_golden(oracle, name):
+    g = load_golden(name)
+    for tag in ("a", "b"):
+        if f"energy_{tag}" not in g:
+            continue
+        delta, cosmax, T = g[f"params_{tag}"]
+        p = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+        bonds, ov = p.total_bonds()
+        assert -bonds == g[f"energy_{tag}"][0] and ov == g[f"energy_{tag}"][1]
+        assert np.array_equal(p.bond_counts()[0], g[f"bond_counts_{tag}"])
+        assert np.array_equal(p.cells(), g[f"ref_cells_{tag}"])
+
+
+def test_known_answers_from_survey(oracle):
+    """fcc.rrr -> -914 (343x4, 143x3, 13x2, 1x1); bcc.rrr -> 0 at delta 0.119, -92 at 0.135."""
+    g = load_golden("fcc")
+    assert g["energy_a"][0] == -914 and g["energy_b"][0] == -914
+    assert list(np.bincount(g["bond_counts_a"])) == [0, 1, 13, 143, 343]
+    g = load_golden("bcc")
+    assert g["energy_a"][0] == 0 and g["energy_b"][0] == -92
+    k = np.load(os.path.join(ROOT, "tests", "golden", "generator_known.npz"))
+    assert k["32768_0.3"][0] == -15 and k["65536_0.5"][0] == -59
+
+
+@pytest.mark.parametrize("name", GOLDEN_SETS)
+def test_port_proposals_golden(oracle, name):
+    g = load_golden(name)
+    delta, cosmax, T = g["params_a"]
+    p = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    dE, ov, acc = p.eval_proposals(g["prop_idx"], g["prop_disp"], g["prop_orient"], g["prop_u"])
+    assert np.array_equal(dE, g["prop_dE"]) and np.array_equal(ov, g["prop_overlap"]) and np.array_equal(acc, g["prop_accept"])
+    n = len(g["seq_dE"])
+    dE, ov, acc = p.eval_proposals(g["prop_idx"][:n], g["prop_disp"][:n], g["prop_orient"][:n], g["prop_u"][:n], commit=True)
+    assert np.array_equal(dE, g["seq_dE"]) and np.array_equal(ov, g["seq_overlap"]) and np.array_equal(acc, g["seq_accept"])
+    r, m = p.state()
+    assert np.array_equal(r, g["seq_r"]) and np.array_equal(m, g["seq_orient"])
+    assert -p.total_bonds()[0] == g["seq_energy"][0]
+
+
+def test_port_vs_reference_library(oracle, tmp_path):
+    """The restatement against the unmodified reference, live (needs oracle/_ref built from /root/reference)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libppref.so not built (no /root/reference here)")
+    g = load_golden("gen2000_rho0.5")
+    rrr = str(tmp_path / "conf.rrr")
+    # write with full precision so that the reference parses back the very same doubles
+    with open(rrr, "w") as f:
+        f.write("0 %d %.17g %.17g %.17g\n" % (len(g["r"]), *g["box"]))
+        for i in range(len(g["r"])):
+            f.write("%.17g %.17g %.17g\n%.17g %.17g %.17g\n%.17g %.17g %.17g\n" % (*g["orient"][i, 0], *g["orient"][i, 1], *g["r"][i]))
+    ref = oracle.RefSystem(rrr, KF_delta=0.2, KF_cosmax=0.85, Temperature=0.12)
+    try:
+        r, m = ref.state()
+        assert np.array_equal(r, g["r"])
+        port = oracle.PortSystem(ref.box(), r, m, kf_delta=0.2, kf_cosmax=0.85, temperature=0.12)
+        e, ov = ref.total_energy()
+        assert (-e, ov) == port.total_bonds()
+        rng = np.random.default_rng(3)
+        n = 3000
+        idx = rng.integers(0, ref.N, n).astype(np.int32)
+        disp = (rng.random((n, 3)) - 0.5) * 0.4
+        u = rng.random(n)
+        orient_new = np.zeros((n, 3, 3))
+        for k in range(n):
+            axis = rng.normal(size=3)
+            axis /= np.linalg.norm(axis)
+            th = rng.random() * 0.6
+            orient_new[k] = ref.rotate(m[idx[k]], axis, th)
+            assert np.array_equal(orient_new[k], oracle.rotate_port(m[idx[k]], axis, th))
+        for commit in (False, True):
+            a = ref.eval_proposals(idx, disp, orient_new, u, commit=commit)
+            b = port.eval_proposals(idx, disp, orient_new, u, commit=commit)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        r1, m1 = ref.state()
+        r2, m2 = port.state()
+        assert np.array_equal(r1, r2) and np.array_equal(m1, m2)
+    finally:
+        ref.close()
+
+
+def test_philox_known_answers(oracle):
+    """Philox4x32-10 known-answer vectors of Random123 (Salmon et al., SC'11)."""
+    L = oracle.port_lib()
+    out = np.zeros(4, dtype=np.uint32)
+    L.ppo_philox4x32(0, 0, 0, 0, 0, 0, out)
+    assert [hex(x) for x in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    L.ppo_philox4x32(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, out)
+    assert [hex(x) for x in out] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    L.ppo_philox4x32(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0, out)
+    assert [hex(x) for x in out] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_rrr_reader_matches_reference_parsing(oracle, tmp_path):
+    import patchyparticles_b200 as pkg
+    g = load_golden("fcc")
+    path = str(tmp_path / "x.rrr")
+    pkg.write_rrr(path, 7, g["box"], g["r"], g["orient"])
+    s1, b1, r1, m1 = pkg.read_rrr(path)
+    s2, b2, r2, m2 = oracle.read_rrr(path)
+    assert s1 == s2 == 7
+    assert np.array_equal(b1, b2) and np.array_equal(r1, r2) and np.array_equal(m1, m2)
+    # same bytes as the C writer that follows output.c:302-317
+    path2 = str(tmp_path / "y.rrr")
+    oracle.write_rrr(path2, 7, g["box"], g["r"], g["orient"])
+    assert open(path).read() == open(path2).read()
+    # header/particle-count mismatch is an error (system.c:245)
+    with open(path, "a") as f:
+        f.write("1 0 0\n0 1 0\n1 1 1\n")
+    with pytest.raises(ValueError):
+        pkg.read_rrr(path)
+
+
+def test_sweep_restatement_invariants(oracle):
+    """ppo_sweep: N attempts per sweep, running bond count == recount, confinement bookkeeping."""
+    import patchyparticles_b200 as pkg
+    box, r, m = pkg.random_fluid(1200, 0.45, seed=5)
+    p = oracle.PortSystem(box, r, m, kf_delta=0.25, kf_cosmax=0.8, temperature=0.15)
+    bonds, ov = p.total_bonds()
+    assert ov == 0
+    st = oracle.SweepStats()
+    for s in range(12):
+        bonds, st = p.sweep(11, s, 0.2, 0.3, bonds, st)
+    assert st.tries == 12 * 1200
+    assert st.tries == st.confined + st.overlapped + (st.tries - st.confined - st.overlapped)
+    assert p.total_bonds() == (bonds, 0)
+    assert 0.05 < st.confined / st.tries < 0.25            # 3 * E|d| / w with d uniform in +-0.1, w ~ 1.3
+    raw = st.accepted / (st.tries - st.confined)
+    est = st.w_accepted / st.w_tries
+    assert abs(raw - est) < 0.02 and 0.2 < est < 0.9
+    # a different seed gives a different trajectory, the same seed the same one
+    q = oracle.PortSystem(box, r, m, kf_delta=0.25, kf_cosmax=0.8, temperature=0.15)
+    b2, _ = q.total_bonds()
+    st2 = oracle.SweepStats()
+    for s in range(12):
+        b2, st2 = q.sweep(11, s, 0.2, 0.3, b2, st2)
+    assert np.array_equal(q.state()[0], p.state()[0]) and b2 == bonds
+
+
+def test_abi_exports_every_declared_symbol():
+    """libpatchy_b200.so loads and exports every function include/pp_b200.h declares (no compute calls)."""
+    import patchyparticles_b200 as pkg
+    header = open(os.path.join(ROOT, "include", "pp_b200.h")).read()
+    declared = set(re.findall(r"\b(pp_[a-zA-Z_0-9]+)\s*\(", header))
+    declared -= {"pp_handle", "pp_params", "pp_observables"}
+    assert declared == set(pkg.engine.ABI_SYMBOLS), declared ^ set(pkg.engine.ABI_SYMBOLS)
+    lib = ctypes.CDLL(pkg.library_path())
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert lib.pp_abi_version() == 1
+    assert ctypes.sizeof(pkg.Params) >= 120
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine refuses to start instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import patchyparticles_b200 as pkg
+    with pytest.raises(Exception) as e:
+        pkg.Engine()
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under patchyparticles_b200/ or host/ may reference it."""
+    bad = []
+    for base in ("patchyparticles_b200", "host", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".c", ".h", "Makefile")):
+                    text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                    if re.search(r'#include\s+"[^"]*oracle|import\s+_oracle|from\s+_oracle|libpporacle|libppref|ppo_[a-z_]+\s*\(', text):
+                        bad.append(os.path.join(dirpath, fn))
+    assert not bad, bad
