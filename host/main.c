@@ -1,0 +1,293 @@
+/*
+ * patchy_b200 -- C host of the B200 Monte Carlo engine.
+ *
+ * Keeps the reference program's contract for the roto-translation path (Dynamics = 0, Ensemble = 0
+ * or 5): one positional argument = input file with the reference's keys, .rrr configurations in and
+ * out, energy.dat / acceptance.dat / density.dat / boxshape.dat and the stdout line in the
+ * reference's formats, Print_every / Save_every / Restart_step_counter semantics and graceful stop on
+ * SIGTERM / SIGABRT / SIGINT / SIGUSR2 (main.c:26-143, output.c:19-211, system.c:58-252).
+ * Every number comes from libpatchy_b200.so (include/pp_b200.h); there is no CPU fallback.
+ *
+ * Extra optional keys: GPU_device, Lanes_per_cell, Shift_every, Lx_reference_sign.
+ */
+#include "../include/pp_b200.h"
+#include "input.h"
+#include "rrr.h"
+
+#include <signal.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+typedef long long llint;
+
+static volatile sig_atomic_t stop_requested = 0;
+
+static void on_signal(int sig) {
+	/* the next time the default handler runs, so the program stays killable (main.c:15-24) */
+	signal(sig, SIG_DFL);
+	static const char msg[] = "# Caught SIGNAL; setting stop = 1\n";
+	if(write(2, msg, sizeof(msg) - 1) < 0) {}
+	stop_requested = 1;
+}
+
+typedef struct {
+	FILE *log, *energy, *density, *acc, *boxshape;
+	llint start_from, print_every, save_every;
+	char conf_folder[512], conf_last[512];
+} host_output;
+
+static void log_msg(host_output *out, const char *fmt, ...) {
+	va_list ap;
+	if(out->log != NULL && out->log != stderr) {
+		va_start(ap, fmt);
+		vfprintf(out->log, fmt, ap);
+		va_end(ap);
+		fflush(out->log);
+	}
+	va_start(ap, fmt);
+	vfprintf(stderr, fmt, ap);
+	va_end(ap);
+}
+
+/* output_exit (output.c:374-388): message to the log and stderr, exit status 1 */
+static void die(host_output *out, const char *fmt, ...) {
+	va_list ap;
+	if(out != NULL && out->log != NULL && out->log != stderr) {
+		va_start(ap, fmt);
+		vfprintf(out->log, fmt, ap);
+		va_end(ap);
+		fflush(out->log);
+	}
+	va_start(ap, fmt);
+	vfprintf(stderr, fmt, ap);
+	va_end(ap);
+	exit(1);
+}
+
+#define PP_CALL(out, h, call) \
+	do { \
+		if((call) != 0) die(out, "%s\n", pp_last_error(h)); \
+	} while(0)
+
+static FILE *open_or_die(host_output *out, const char *name, const char *mode, const char *what) {
+	FILE *f = fopen(name, mode);
+	if(f == NULL) die(out, "%s file '%s' is not writable\n", what, name);
+	return f;
+}
+
+static void save_configuration(host_output *out, pp_handle *h, int N, llint step, const char *name, double *r, double *orient) {
+	pp_observables obs;
+	PP_CALL(out, h, pp_download(h, r, orient));
+	PP_CALL(out, h, pp_get_observables(h, &obs, 0));
+	if(pph_rrr_write(name, step, N, obs.box, r, orient) != 0) die(out, "File '%s' is not writable\n", name);
+}
+
+/* output_print (output.c:119-211) */
+static void print_observables(host_output *out, pp_handle *h, const pp_params *prm, llint step) {
+	pp_observables o;
+	PP_CALL(out, h, pp_get_observables(h, &o, 1)); /* counters are reset after each print (output.c:189) */
+	const double V = o.box[0] * o.box[1] * o.box[2];
+	const double E = (o.N > 0) ? o.energy / o.N : 0.;
+	fprintf(out->energy, "%lld %lf\n", step, E);
+	fflush(out->energy);
+	if(prm->ensemble != PP_NVT) {
+		fprintf(out->density, "%lld %lf %d\n", step, o.N / V, o.N);
+		fflush(out->density);
+	}
+	if(prm->Lx_move) {
+		fprintf(out->boxshape, "%lld %lf %lf %lf\n", step, o.box[0], o.box[1], o.box[2]);
+		fflush(out->boxshape);
+	}
+	/* accepted / tries per move type; the roto-translation column is the engine's estimator of the same
+	 * ratio (cell-confined proposals are geometry, not physics: DESIGN.md "acceptance estimator") */
+	const double zero = 0.;
+	const double acc_roto = (o.tries[PP_ROTO_TRASL] > 0) ? o.acceptance_roto : zero / zero;
+	fprintf(out->acc, "%lld %e", step, acc_roto);
+	if(prm->ensemble == PP_NPT) fprintf(out->acc, " %e", o.accepted[PP_VOLUME] / (double) o.tries[PP_VOLUME]);
+	if(prm->Lx_move) fprintf(out->acc, " %e", o.accepted[PP_LX] / (double) o.tries[PP_LX]);
+	fprintf(out->acc, "\n");
+	fflush(out->acc);
+	printf("%lld %lf %lf", step, E, o.energy);
+	if(prm->ensemble != PP_NVT) printf(" %lf", o.N / V);
+	printf("\n");
+	fflush(stdout);
+}
+
+int main(int argc, char *argv[]) {
+	host_output out;
+	memset(&out, 0, sizeof(out));
+	out.log = stderr;
+	if(argc < 2) die(&out, "Usage is %s input\n", argv[0]);
+
+	signal(SIGTERM, on_signal);
+	signal(SIGABRT, on_signal);
+	signal(SIGINT, on_signal);
+	signal(SIGUSR2, on_signal);
+
+	pph_input *in = pph_input_load(argv[1]);
+	if(in == NULL) {
+		fprintf(stderr, "Input file not found\n");
+		return 1;
+	}
+
+	/* ---- output_init (output.c:19-117) ----------------------------------------------------- */
+	int restart_step_counter = 1;
+	pph_get_int(in, "Restart_step_counter", &restart_step_counter, 0);
+	const char *mode = restart_step_counter ? "w" : "a";
+	char name[1100], conf_name[512];
+	if(pph_get_string(in, "Log_file", name, sizeof(name), 0) && strcmp(name, "none") != 0) {
+		out.log = fopen(name, "a");
+		if(out.log == NULL) {
+			out.log = stderr;
+			die(&out, "Log file '%s' is not writable\n", name);
+		}
+	}
+	pph_get_string(in, "Initial_conditions_file", conf_name, sizeof(conf_name), 1);
+	pph_get_llint(in, "Print_every", &out.print_every, 1);
+	pph_get_llint(in, "Save_every", &out.save_every, 1);
+	if(out.print_every < 1 || out.save_every < 1) die(&out, "Print_every and Save_every must be positive\n");
+	snprintf(name, sizeof(name), "energy.dat");
+	pph_get_string(in, "Energy_file", name, sizeof(name), 0);
+	out.energy = open_or_die(&out, name, mode, "Energy");
+	snprintf(name, sizeof(name), "acceptance.dat");
+	pph_get_string(in, "Acceptance_file", name, sizeof(name), 0);
+	out.acc = open_or_die(&out, name, mode, "Acceptance");
+	pph_get_string(in, "Configuration_folder", out.conf_folder, sizeof(out.conf_folder), 1);
+	if(access(out.conf_folder, W_OK) != 0)
+		die(&out, "Cannot create files in directory '%s': please make sure that the directory exists and it is writable\n", out.conf_folder);
+	snprintf(out.conf_last, sizeof(out.conf_last), "last.rrr");
+	pph_get_string(in, "Configuration_last", out.conf_last, sizeof(out.conf_last), 0);
+
+	/* ---- system_init (system.c:58-252) ----------------------------------------------------- */
+	pp_params prm;
+	pp_default_params(&prm);
+	int dynamics = 0, seed = 0, itmp = 0;
+	pph_get_int(in, "Dynamics", &dynamics, 1);
+	pph_get_int(in, "Ensemble", &prm.ensemble, 1);
+	pph_get_double(in, "Disp_max", &prm.disp_max, 1);
+	pph_get_double(in, "Theta_max", &prm.theta_max, 1);
+	pph_get_double(in, "Temperature", &prm.temperature, 1);
+	if(!pph_get_int(in, "Seed", &seed, 0)) {
+		seed = (int) time(NULL);
+		log_msg(&out, "Using seed %d\n", seed);
+	}
+	prm.seed = (uint64_t) (unsigned int) seed;
+	pph_get_double(in, "KF_delta", &prm.kf_delta, 1);
+	pph_get_double(in, "KF_cosmax", &prm.kf_cosmax, 1);
+	log_msg(&out, "Patch parameters: cosmax = %lf, delta = %lf\n", prm.kf_cosmax, prm.kf_delta);
+	if(dynamics != 0) die(&out, "Dynamics %d not supported on the GPU path (only 0, roto-translations; VMMC/AVB stay on the CPU reference)\n", dynamics);
+	if(prm.ensemble != PP_NVT && prm.ensemble != PP_NPT)
+		die(&out, "Ensemble %d not supported on the GPU path (0 = NVT, 5 = NPT; GC/SUS/BSUS stay on the CPU reference)\n", prm.ensemble);
+	if(prm.ensemble != PP_NVT) {
+		snprintf(name, sizeof(name), "density.dat");
+		pph_get_string(in, "Density_file", name, sizeof(name), 0);
+		out.density = open_or_die(&out, name, mode, "Density");
+	}
+
+	llint conf_step = 0;
+	int N = 0, found = 0;
+	double box[3], *r = NULL, *orient = NULL;
+	int rc = pph_rrr_read(conf_name, &conf_step, &N, box, &r, &orient, &found);
+	if(rc == -1) die(&out, "Initial_conditions_file '%s' is not readable\n", conf_name);
+	if(rc == -2) die(&out, "The initial configuration file '%s' is empty or its headers are malformed\n", conf_name);
+	if(rc == -3) die(&out, "Number of particles found in configuration (%d) is different from the value found in the header (%d)\n", found, N);
+	out.start_from = restart_step_counter ? 0 : conf_step;
+
+	if(prm.ensemble == PP_NPT) {
+		pph_get_double(in, "rescale_factor_max", &prm.rescale_factor_max, 1);
+		pph_get_double(in, "P", &prm.P, 1);
+	}
+	else {
+		pph_get_int(in, "Lx_move", &prm.Lx_move, 0);
+		if(prm.Lx_move) {
+			if(box[1] != box[2]) die(&out, "Lx_move = 1 requires Ly = Lz\n");
+			pph_get_double(in, "Lx_change_max", &prm.Lx_change_max, 1);
+			pph_get_double(in, "Lyz_min", &prm.Lyz_min, 1);
+			pph_get_double(in, "Lyz_max", &prm.Lyz_max, 1);
+			if(prm.Lyz_min >= box[1]) die(&out, "Lyz_min should be smaller than box size\n");
+			if(prm.Lyz_max <= box[1]) die(&out, "Lyz_max should be larger than box size\n");
+			log_msg(&out, "Ly and Lz are allowed to vary between %lf and %lf\n", prm.Lyz_min, prm.Lyz_max);
+			out.boxshape = open_or_die(&out, "boxshape.dat", mode, "boxshape.dat");
+		}
+	}
+	if(pph_get_int(in, "GPU_device", &itmp, 0)) prm.device = itmp;
+	if(pph_get_int(in, "Lanes_per_cell", &itmp, 0)) prm.lanes_per_cell = itmp;
+	if(pph_get_int(in, "Shift_every", &itmp, 0)) prm.shift_every = itmp;
+	if(pph_get_int(in, "Lx_reference_sign", &itmp, 0)) prm.Lx_reference_sign = itmp;
+
+	pp_handle *h = NULL;
+	if(pp_create(&prm, &h) != 0) die(&out, "%s\n", pp_last_error(h));
+	PP_CALL(&out, h, pp_upload(h, N, box, r, orient));
+	{
+		pp_observables o;
+		PP_CALL(&out, h, pp_get_observables(h, &o, 0));
+		log_msg(&out, "Cells per side: (%d, %d, %d), total: %d\n", o.n_side[0], o.n_side[1], o.n_side[2], o.n_side[0] * o.n_side[1] * o.n_side[2]);
+	}
+
+	/* ---- initial energy and overlap check (main.c:55-64) ------------------------------------- */
+	llint bonds = 0;
+	int overlap = 0;
+	PP_CALL(&out, h, pp_total_bonds(h, &bonds, &overlap));
+	if(overlap) die(&out, "Initial configuration contains an overlap, aborting\n");
+	log_msg(&out, "Initial energy: %lf\n", (N > 0) ? -(double) bonds / N : 0.);
+
+	llint steps = 0;
+	pph_get_llint(in, "Steps", &steps, 1);
+	steps += out.start_from;
+
+	/* ---- main loop (main.c:78-120) -------------------------------------------------------------- */
+	llint step = out.start_from;
+	while(step < steps && !stop_requested) {
+		if(step % out.print_every == 0) {
+			print_observables(&out, h, &prm, step);
+			save_configuration(&out, h, N, step, out.conf_last, r, orient);
+			if(step != 0) { /* MC_check_energy + cells_check (main.c:85-87) */
+				llint scratch;
+				int ov, ok;
+				PP_CALL(&out, h, pp_check_energy(h, &scratch, &ov, &ok));
+				if(ov) die(&out, "\nComputing energy from scratch resulted in an overlap, aborting\n");
+				if(!ok) die(&out, "\nEnergy check failed: %s\n", pp_last_error(h));
+			}
+		}
+		if(step > 0 && step % out.save_every == 0) {
+			snprintf(name, sizeof(name), "%s/conf_%lld.rrr", out.conf_folder, step);
+			save_configuration(&out, h, N, step, name, r, orient);
+			save_configuration(&out, h, N, step, out.conf_last, r, orient);
+		}
+		/* run up to the next print / save point, in chunks short enough to notice a signal */
+		llint next = steps;
+		const llint np = (step / out.print_every + 1) * out.print_every, ns = (step / out.save_every + 1) * out.save_every;
+		if(np < next) next = np;
+		if(ns < next) next = ns;
+		llint chunk = next - step;
+		if(chunk > 64) chunk = 64;
+		PP_CALL(&out, h, pp_sweep(h, chunk));
+		PP_CALL(&out, h, pp_sync(h));
+		step += chunk;
+	}
+
+	/* ---- last configuration and last line (main.c:125-132) ------------------------------------ */
+	save_configuration(&out, h, N, step, out.conf_last, r, orient);
+	{
+		pp_observables o;
+		PP_CALL(&out, h, pp_get_observables(h, &o, 0));
+		printf("%lld %lf %lf", step, (o.N > 0) ? o.energy / o.N : 0., o.energy);
+		if(prm.ensemble != PP_NVT) printf(" %lf", o.N / (o.box[0] * o.box[1] * o.box[2]));
+		printf("\n");
+	}
+
+	pp_destroy(h);
+	free(r);
+	free(orient);
+	fclose(out.energy);
+	fclose(out.acc);
+	if(out.density) fclose(out.density);
+	if(out.boxshape) fclose(out.boxshape);
+	if(out.log != stderr) fclose(out.log);
+	pph_input_free(in);
+	return 0;
+}

@@ -1,0 +1,145 @@
+"""The C host (host/patchy_b200) against the unmodified reference program (oracle/_ref/PatchyParticles)
+fed with the SAME input file: output formats, and statistical agreement of <E>/N, acceptance and (NPT)
+density within 3 sigma of block-averaged error bars (BASELINE.json north_star).
+
+Parallel checkerboard dynamics is a different Markov chain from the reference's random sequential
+picks, so trajectories cannot be compared move by move; equilibrium averages must agree.  The state
+points are chosen where the reference equilibrates in a few thousand steps (SURVEY.md section 7,
+hard part 3): a T = 0.2 / cosmax = 0.92 fluid for NVT and a T = 0.3 fluid at P = 0.3 for NPT.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "PatchyParticles")
+GEN_BIN = os.path.join(ROOT, "oracle", "_ref", "generator")
+HOST_BIN = os.path.join(ROOT, "host", "patchy_b200")
+
+
+def need_binaries():
+    for b in (REF_BIN, GEN_BIN, HOST_BIN):
+        if not os.path.exists(b):
+            pytest.skip(f"{b} not built")
+
+
+def write_input(path, **keys):
+    with open(path, "w") as f:
+        for k, v in keys.items():
+            f.write(f"{k} = {v}\n")
+
+
+def run(binary, workdir):
+    p = subprocess.run([binary, "input"], cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+def block_stats(x, n_blocks=10):
+    x = np.asarray(x, dtype=float)
+    n = (len(x) // n_blocks) * n_blocks
+    means = x[:n].reshape(n_blocks, -1).mean(axis=1)
+    return means.mean(), means.std(ddof=1) / np.sqrt(n_blocks)
+
+
+def load_cols(path):
+    return np.loadtxt(path, ndmin=2)
+
+
+def make_case(tmp_path, N, rho, **keys):
+    d_ref, d_gpu = tmp_path / "ref", tmp_path / "gpu"
+    for d in (d_ref, d_gpu):
+        d.mkdir()
+    subprocess.run([GEN_BIN, str(N), str(rho)], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    base = dict(Dynamics=0, Ensemble=0, Temperature=0.2, Steps=100, Disp_max=0.2, Theta_max=0.3,
+                Initial_conditions_file=str(tmp_path / "generated.rrr"), Print_every=20, Save_every=100000000,
+                Configuration_folder=".", KF_delta=0.119, KF_cosmax=0.92, Seed=12345, Log_file="none")
+    base.update(keys)
+    write_input(d_ref / "input", **base)
+    write_input(d_gpu / "input", **base)
+    return d_ref, d_gpu
+
+
+def test_host_output_formats(tmp_path):
+    """Same files, same columns, same step stamps as the reference program; last.rrr is loadable."""
+    need_binaries()
+    import patchyparticles_b200 as pkg
+    d_ref, d_gpu = make_case(tmp_path, 1000, 0.3, Steps=100, Print_every=20, Save_every=50)
+    out_ref, out_gpu = run(REF_BIN, d_ref), run(HOST_BIN, d_gpu)
+    for fn in ("energy.dat", "acceptance.dat", "last.rrr", "conf_50.rrr"):
+        assert (d_gpu / fn).exists(), fn
+    e_ref, e_gpu = load_cols(d_ref / "energy.dat"), load_cols(d_gpu / "energy.dat")
+    assert e_ref.shape == e_gpu.shape and np.array_equal(e_ref[:, 0], e_gpu[:, 0])
+    assert e_ref[0, 1] == e_gpu[0, 1]  # same initial configuration -> same initial energy line
+    a_ref = open(d_ref / "acceptance.dat").read().split("\n")
+    a_gpu = open(d_gpu / "acceptance.dat").read().split("\n")
+    assert a_ref[0] == a_gpu[0] == "0 -nan"  # first row is 0/0 in both programs (output.c:148-189)
+    assert len(a_ref) == len(a_gpu)
+    assert len(out_ref.strip().split("\n")) == len(out_gpu.strip().split("\n"))
+    assert [len(l.split()) for l in out_ref.strip().split("\n")] == [len(l.split()) for l in out_gpu.strip().split("\n")]
+    step, box, r, m = pkg.read_rrr(str(d_gpu / "last.rrr"))
+    assert step == 100 and len(r) == 1000
+    head_ref = open(d_ref / "last.rrr").readline().split()
+    head_gpu = open(d_gpu / "last.rrr").readline().split()
+    assert head_ref == head_gpu  # NVT: same step, N and box, same formatting
+    # error convention: fatal message + exit status 1 (output.c:374-388), missing mandatory key -> exit(-1)
+    write_input(d_gpu / "input", Dynamics=1, Ensemble=0, Temperature=0.2, Steps=1, Disp_max=0.1, Theta_max=0.1,
+                Initial_conditions_file=str(tmp_path / "generated.rrr"), Print_every=1, Save_every=1, Configuration_folder=".",
+                KF_delta=0.119, KF_cosmax=0.92)
+    p = subprocess.run([HOST_BIN, "input"], cwd=d_gpu, capture_output=True, text=True)
+    assert p.returncode == 1 and "not supported" in p.stderr
+    write_input(d_gpu / "input", Dynamics=0, Ensemble=0)
+    p = subprocess.run([HOST_BIN, "input"], cwd=d_gpu, capture_output=True, text=True)
+    assert p.returncode == 255 and "Mandatory key" in p.stderr
+
+
+def test_nvt_statistics_vs_reference(tmp_path):
+    """<E>/N and roto-translation acceptance at equilibrium, N = 1000, rho = 0.3, T = 0.2, cosmax = 0.92."""
+    need_binaries()
+    d_ref, d_gpu = make_case(tmp_path, 1000, 0.3, Steps=12000)
+    run(REF_BIN, d_ref)
+    write_input(d_gpu / "input", **dict(Dynamics=0, Ensemble=0, Temperature=0.2, Steps=24000, Disp_max=0.2, Theta_max=0.3,
+                Initial_conditions_file=str(tmp_path / "generated.rrr"), Print_every=20, Save_every=100000000,
+                Configuration_folder=".", KF_delta=0.119, KF_cosmax=0.92, Seed=777, Log_file="none"))
+    run(HOST_BIN, d_gpu)
+    discard = 4000
+    res = {}
+    for tag, d in (("ref", d_ref), ("gpu", d_gpu)):
+        e = load_cols(d / "energy.dat")
+        a = load_cols(d / "acceptance.dat")
+        res[tag] = (block_stats(e[e[:, 0] >= discard, 1]), block_stats(a[a[:, 0] >= discard, 1]))
+    (e_ref, se_ref), (a_ref, sa_ref) = res["ref"]
+    (e_gpu, se_gpu), (a_gpu, sa_gpu) = res["gpu"]
+    print(f"E/N ref {e_ref:.4f} +- {se_ref:.4f}   gpu {e_gpu:.4f} +- {se_gpu:.4f}")
+    print(f"acc ref {a_ref:.4f} +- {sa_ref:.4f}   gpu {a_gpu:.4f} +- {sa_gpu:.4f}")
+    assert -0.9 < e_ref < -0.5  # the state point is the bonded fluid it is meant to be
+    assert abs(e_gpu - e_ref) < 3.0 * np.hypot(se_ref, se_gpu)
+    assert abs(a_gpu - a_ref) < 3.0 * np.hypot(sa_ref, sa_gpu)
+
+
+def test_npt_statistics_vs_reference(tmp_path):
+    """Density (and volume-move acceptance) under NPT, N = 300, T = 0.3, P = 0.3."""
+    need_binaries()
+    keys = dict(Ensemble=5, Temperature=0.3, P=0.3, rescale_factor_max=0.03, KF_cosmax=0.98, Print_every=10)
+    d_ref, d_gpu = make_case(tmp_path, 300, 0.38, Steps=30000, **keys)
+    run(REF_BIN, d_ref)
+    run(HOST_BIN, d_gpu)
+    discard = 3000
+    res = {}
+    for tag, d in (("ref", d_ref), ("gpu", d_gpu)):
+        rho = load_cols(d / "density.dat")
+        a = load_cols(d / "acceptance.dat")
+        assert a.shape[1] == 3  # step, roto, volume
+        res[tag] = (block_stats(rho[rho[:, 0] >= discard, 1]), block_stats(a[a[:, 0] >= discard, 1]))
+    (r_ref, sr_ref), (a_ref, sa_ref) = res["ref"]
+    (r_gpu, sr_gpu), (a_gpu, sa_gpu) = res["gpu"]
+    print(f"rho ref {r_ref:.4f} +- {sr_ref:.4f}   gpu {r_gpu:.4f} +- {sr_gpu:.4f}")
+    print(f"acc ref {a_ref:.4f} +- {sa_ref:.4f}   gpu {a_gpu:.4f} +- {sa_gpu:.4f}")
+    assert 0.35 < r_ref < 0.45
+    assert abs(r_gpu - r_ref) < 3.0 * np.hypot(sr_ref, sr_gpu)
+    assert abs(a_gpu - a_ref) < 3.0 * np.hypot(sa_ref, sa_gpu)
