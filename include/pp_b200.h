@@ -143,6 +143,33 @@ int pp_set_profiling(pp_handle *h, int enable);
 int pp_kernel_stats(pp_handle *h, int kclass, long long *launches, double *ms_total);
 int pp_reset_kernel_stats(pp_handle *h);
 
+/* ---- x-slab decomposition across the GPUs of one box (one engine per GPU) -------------------------
+ * The reference has no decomposition (single thread, main.c:26-143); this is the scale-out axis of
+ * the engine for large N.  Each engine owns whole pairs of x layers of the global cell grid plus one
+ * halo layer per side.  pp_slab_setup is called before pp_upload (every engine receives the whole
+ * configuration and keeps its layers).  pp_total_bonds / pp_get_observables / pp_check_energy then
+ * return this engine's contribution (a cross-boundary pair is counted by the engine on its left);
+ * the driver sums over engines.  One sweep is driven as
+ *     pp_slab_sweep_begin(&exchange)
+ *     if exchange:  send pp_slab_outbox(side) to the neighbour on that side, receive into
+ *                   pp_slab_inbox(side, count), then pp_slab_sweep_rebuild()
+ *     pp_slab_pass_block(0);  first owned layer -> left neighbour's right halo   (pp_slab_halo views)
+ *     pp_slab_pass_block(1);  last owned layer  -> right neighbour's left halo
+ *     pp_slab_sweep_end()
+ * Records are 13 doubles (x, y, z, id, orientation[9]); halo views are contiguous slices of the
+ * engine's position (double4), orientation (9 doubles) and FP32 shadow (float4) arrays.  All
+ * pointers returned here are DEVICE pointers.  NVT only. */
+int pp_slab_setup(pp_handle *h, int rank, int world);
+int pp_slab_range(pp_handle *h, int *x0, int *x1, int *nx, int *n_local);
+int pp_slab_sweep_begin(pp_handle *h, int *exchange);
+int pp_slab_outbox(pp_handle *h, int side, void **dev, int *count);
+int pp_slab_inbox(pp_handle *h, int side, int count, void **dev);
+int pp_slab_sweep_rebuild(pp_handle *h);
+int pp_slab_pass_block(pp_handle *h, int cx);
+int pp_slab_halo(pp_handle *h, int side, int recv, void **pos, void **ori, void **posf, int *count);
+int pp_slab_sweep_end(pp_handle *h);
+int pp_slab_download(pp_handle *h, int *n_owned, int *ids, double *r, double *orient);
+
 #ifdef __cplusplus
 }
 #endif

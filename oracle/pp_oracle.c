@@ -572,7 +572,8 @@ void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep, int shift_every, do
 
 	int colour;
 	for(colour = 0; colour < 8; colour++) {
-		int ox = colour & 1, oy = (colour >> 1) & 1, oz = (colour >> 2) & 1;
+		/* pass order: x parity slowest, so that a slab decomposition along x exchanges halos twice per sweep */
+		int ox = (colour >> 2) & 1, oy = (colour >> 1) & 1, oz = colour & 1;
 		int ix, iy, iz;
 		for(ix = ox; ix < n_side[0]; ix += 2)
 			for(iy = oy; iy < n_side[1]; iy += 2)

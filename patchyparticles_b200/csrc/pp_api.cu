@@ -87,6 +87,19 @@ struct pp_handle {
 	long long tries[PP_N_MOVES], accepted[PP_N_MOVES];
 	uint64_t box_draws;
 
+	// x-slab decomposition (one engine per GPU; world == 1: the whole periodic box)
+	int slab_rank, slab_world;
+	int x0, x1;          // global x layers [x0, x1) owned by this engine
+	int nxl;             // layers held: owned + 2 halo layers (n_side[0] when world == 1)
+	int N_global;        // particles of the whole system
+	double *outbox[2], *inbox[2]; // migration / halo records (13 doubles each) to / from the left (0) and right (1) neighbour
+	int cap_records;
+	int *d_slab_counts;  // keep, left, right, error
+	int keep_count, out_count[2], in_count[2];
+	double pending_shift[3];
+	bool slab_pending;   // a classify has been done and waits for pp_slab_sweep_rebuild
+	int layer_slots[6];  // slot offsets: left halo begin, first owned begin, first owned end, last owned begin, right halo begin, right halo end
+
 	// profiling
 	bool profiling;
 	long long launches[PP_K_CLASSES];
@@ -217,6 +230,20 @@ SimConst make_const(const pp_handle *h, const double *box, const double *shift) 
 	}
 	sc.n_cells = h->n_cells;
 	sc.N = h->N;
+	if(h->slab_world > 1) {
+		sc.slab = 1;
+		sc.nxl = h->nxl;
+		sc.x_lo = (h->x0 - 1 + h->n_side[0]) % h->n_side[0];
+		sc.own_lo = 1;
+		sc.own_hi = h->nxl - 1;
+	}
+	else {
+		sc.slab = 0;
+		sc.nxl = h->n_side[0];
+		sc.x_lo = 0;
+		sc.own_lo = 0;
+		sc.own_hi = h->n_side[0];
+	}
 	sc.sqr_rcut = (1. + h->prm.kf_delta) * (1. + h->prm.kf_delta); // system.c:86
 	sc.cosmax = h->prm.kf_cosmax;
 	sc.cos2_lo = sc.cosmax * sc.cosmax * (1. - 1e-11);
@@ -258,11 +285,27 @@ void prof_end(pp_handle *h, int kclass, int n_launches) {
 	}
 }
 
+// slab decomposition: after a sort, particles outside the held layers sit in the trash cell at the end of the
+// arrays and are dropped; the slot ranges of the boundary and halo layers are cached for the halo refresh
+int slab_after_sort(pp_handle *h) {
+	const int nyz = h->n_side[1] * h->n_side[2];
+	const int idx[7] = {0, nyz, 2 * nyz, (h->nxl - 2) * nyz, (h->nxl - 1) * nyz, h->nxl * nyz, h->n_cells + 1};
+	int val[7];
+	for(int k = 0; k < 7; k++) CUDA_OK(h, cudaMemcpyAsync(&val[k], h->cb.cell_start + idx[k], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CUDA_OK(h, cudaStreamSynchronize(h->stream));
+	for(int k = 0; k < 6; k++) h->layer_slots[k] = val[k];
+	h->N = val[5]; // everything before the trash cell
+	return 0;
+}
+
 // K1 on the current state with the given grid shift; the sorted copy becomes current.
 int rebin(pp_handle *h, const double *shift) {
-	if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", h->box[0], h->box[1], h->box[2], h->r_cut);
-	h->n_cells = h->n_side[0] * h->n_side[1] * h->n_side[2];
-	if(ensure_cells(h, (size_t) h->n_cells)) return 1;
+	if(h->slab_world <= 1) {
+		if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", h->box[0], h->box[1], h->box[2], h->r_cut);
+		h->nxl = h->n_side[0];
+	}
+	h->n_cells = h->nxl * h->n_side[1] * h->n_side[2];
+	if(ensure_cells(h, (size_t) h->n_cells + 2)) return 1;
 	memcpy(h->shift, shift, sizeof(h->shift));
 	const SimConst sc = make_const(h, h->box, h->shift);
 	const int np = (h->cp + 1) % 3, no = h->co ^ 1;
@@ -274,6 +317,7 @@ int rebin(pp_handle *h, const double *shift) {
 	h->cells_valid = true;
 	h->sweep_grid = false;
 	CUDA_OK(h, cudaGetLastError());
+	if(h->slab_world > 1 && slab_after_sort(h)) return 1;
 	return 0;
 }
 
@@ -538,6 +582,11 @@ int pp_destroy(pp_handle *h) {
 	free_cells(h);
 	cudaFree(h->d_counters);
 	cudaFree(h->cb.bins);
+	for(int k = 0; k < 2; k++) {
+		cudaFree(h->outbox[k]);
+		cudaFree(h->inbox[k]);
+	}
+	cudaFree(h->d_slab_counts);
 	cudaFreeHost(h->h_counters);
 	if(h->ev0) cudaEventDestroy(h->ev0);
 	if(h->ev1) cudaEventDestroy(h->ev1);
@@ -583,8 +632,28 @@ int pp_upload(pp_handle *h, int N, const double *box, const double *r, const dou
 	for(int k = 0; k < 3; k++)
 		if(!(box[k] > 0.)) return fail(h, "box side %d is not positive", k);
 	h->N = N;
+	h->N_global = N;
 	memcpy(h->box, box, sizeof(h->box));
 	if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", box[0], box[1], box[2], h->r_cut);
+	h->nxl = h->n_side[0];
+	if(h->slab_world > 1) {
+		// whole pairs of x layers per engine: every engine's first owned layer is even, its last one odd
+		const int pairs = h->n_side[0] / 2, base = pairs / h->slab_world, rem = pairs % h->slab_world, r_ = h->slab_rank;
+		if(base < 1) return fail(h, "%d x layers cannot be split over %d engines (at least 2 layers each)", h->n_side[0], h->slab_world);
+		h->x0 = 2 * (r_ * base + (r_ < rem ? r_ : rem));
+		h->x1 = h->x0 + 2 * (base + (r_ < rem ? 1 : 0));
+		h->nxl = (h->x1 - h->x0) + 2;
+		if(h->prm.ensemble != PP_NVT || h->prm.Lx_move) return fail(h, "the slab decomposition supports NVT roto-translations only (box moves: single engine)");
+		h->cap_records = 4 * (N / h->n_side[0] + 1) + 8192;
+		for(int k = 0; k < 2; k++) {
+			cudaFree(h->outbox[k]);
+			cudaFree(h->inbox[k]);
+			CUDA_OK(h, cudaMalloc(&h->outbox[k], sizeof(double) * 13 * (size_t) h->cap_records));
+			CUDA_OK(h, cudaMalloc(&h->inbox[k], sizeof(double) * 13 * (size_t) h->cap_records));
+		}
+		if(h->d_slab_counts == nullptr) CUDA_OK(h, cudaMalloc(&h->d_slab_counts, 4 * sizeof(int)));
+		h->slab_pending = false;
+	}
 	if(ensure_state(h, (size_t) N)) return 1;
 	if(N > 0) {
 		CUDA_OK(h, cudaMemcpyAsync(h->d_stage_r, r, sizeof(double) * 3 * (size_t) N, cudaMemcpyHostToDevice, h->stream));
@@ -610,6 +679,7 @@ int pp_upload(pp_handle *h, int N, const double *box, const double *r, const dou
 
 int pp_download(pp_handle *h, double *r, double *orient) {
 	if(h == nullptr) return 1;
+	if(h->slab_world > 1) return fail(h, "slab decomposition: use pp_slab_download");
 	if(h->N == 0) return 0;
 	launch_unpack_state(h->N, h->pos[h->cp], h->ori[h->co], h->pid[h->co], h->d_stage_r, h->d_stage_o, h->stream);
 	CUDA_OK(h, cudaMemcpyAsync(r, h->d_stage_r, sizeof(double) * 3 * (size_t) h->N, cudaMemcpyDeviceToHost, h->stream));
@@ -647,6 +717,7 @@ int pp_bond_counts(pp_handle *h, int *counts) {
 
 int pp_sweep(pp_handle *h, long long nsteps) {
 	if(h == nullptr) return 1;
+	if(h->slab_world > 1) return fail(h, "slab decomposition: drive the sweep with pp_slab_sweep_begin / _rebuild / _pass_block / _sweep_end");
 	if(h->N == 0) {
 		h->step += nsteps;
 		return 0;
@@ -693,7 +764,9 @@ int pp_sweep(pp_handle *h, long long nsteps) {
 		int lanes = h->prm.lanes_per_cell;
 		if(lanes == 0) lanes = (h->N >= 400000) ? 8 : 16; // measured on B200: profiles/README.md
 		if(lanes == 1 && (h->n_side[0] < 4 || h->n_side[1] < 4 || h->n_side[2] < 4)) lanes = 8;
-		for(int colour = 0; colour < 8; colour++) {
+		for(int pass = 0; pass < 8; pass++) {
+			// pass order: x parity slowest (a slab decomposition along x then exchanges halos twice per sweep)
+			const int colour = ((pass >> 2) & 1) | (((pass >> 1) & 1) << 1) | ((pass & 1) << 2);
 			if(lanes == 1) nl += launch_sweep_cells(sc, colour, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
 			else nl += launch_sweep_pass(sc, colour, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
 		}
@@ -716,7 +789,7 @@ int pp_get_observables(pp_handle *h, pp_observables *obs, int reset) {
 	const Counters &c = *h->h_counters;
 	memset(obs, 0, sizeof(*obs));
 	obs->step = h->step;
-	obs->N = h->N;
+	obs->N = (h->slab_world > 1) ? h->N_global : h->N;
 	memcpy(obs->box, h->box, sizeof(obs->box));
 	obs->energy = -(double) running_bonds(h);
 	for(int k = 0; k < PP_N_MOVES; k++) {
@@ -760,8 +833,9 @@ int pp_check_energy(pp_handle *h, long long *bonds_scratch, int *overlap, int *o
 	int good = 1;
 	if(ov) good = 0;
 	const double E_run = -(double) running, E_new = -(double) b;
-	if(h->bonds_known && fabs(E_run) > 1e-5 && fabs((E_new - E_run) / E_run) > 1e-5) good = 0; // MC.c:779
-	if(total != h->N) good = 0;
+	// (with a slab decomposition only the sum over engines is comparable: the driver checks it)
+	if(h->slab_world <= 1 && h->bonds_known && fabs(E_run) > 1e-5 && fabs((E_new - E_run) / E_run) > 1e-5) good = 0; // MC.c:779
+	if(h->slab_world <= 1 && total != h->N) good = 0;
 	// E <- E_scratch (MC.c:783)
 	h->bonds_base = b - h->h_counters->dbonds;
 	h->bonds_known = true;
@@ -775,6 +849,7 @@ int pp_check_energy(pp_handle *h, long long *bonds_scratch, int *overlap, int *o
 int pp_eval_proposals(pp_handle *h, int n, const int *idx, const double *disp, const double *orient_new, const double *u, int commit, int *dE,
 		int *overlap, int *accept) {
 	if(h == nullptr) return 1;
+	if(h->slab_world > 1) return fail(h, "pp_eval_proposals is a single-engine test hook");
 	if(n <= 0) return 0;
 	for(int k = 0; k < n; k++)
 		if(idx[k] < 0 || idx[k] >= h->N) return fail(h, "proposal %d: particle index %d out of range", k, idx[k]);
@@ -859,6 +934,164 @@ int pp_Lx_move(pp_handle *h, double u_lx, double u_acc, int *accepted) {
 	int acc = 0;
 	if(Lx_move(h, u_lx, u_acc, &acc)) return 1;
 	if(accepted) *accepted = acc;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// x-slab decomposition hooks (one engine per GPU).  The driver (patchyparticles_b200/slab.py under
+// torchrun, or any host with a transport) moves the outbox / halo buffers between neighbours.
+// ---------------------------------------------------------------------------------------------------
+int pp_slab_setup(pp_handle *h, int rank, int world) {
+	if(h == nullptr) return 1;
+	if(world < 1 || rank < 0 || rank >= world) return fail(h, "bad slab rank %d / world %d", rank, world);
+	h->slab_rank = rank;
+	h->slab_world = world;
+	return 0;
+}
+
+int pp_slab_range(pp_handle *h, int *x0, int *x1, int *nx, int *n_local) {
+	if(h == nullptr) return 1;
+	if(x0) *x0 = (h->slab_world > 1) ? h->x0 : 0;
+	if(x1) *x1 = (h->slab_world > 1) ? h->x1 : h->n_side[0];
+	if(nx) *nx = h->n_side[0];
+	if(n_local) *n_local = h->N;
+	return 0;
+}
+
+int pp_slab_sweep_begin(pp_handle *h, int *exchange) {
+	if(h == nullptr || exchange == nullptr) return 1;
+	if(h->slab_world <= 1) return fail(h, "pp_slab_sweep_begin without a slab decomposition");
+	CUDA_OK(h, cudaSetDevice(h->device));
+	*exchange = 0;
+	const long long period = h->prm.shift_every;
+	if(h->sweep_grid && h->cells_valid && h->step % period != 0) return 0;
+	// new shift period: same stream as the single-engine path, so every engine draws the same shift
+	const uint64_t epoch = (uint64_t) (h->step / period);
+	uint32_t x[4];
+	philox_host(kTagShift, 0u, (uint32_t) epoch, (uint32_t) ((epoch >> 32) << 8), (uint32_t) h->prm.seed, (uint32_t) (h->prm.seed >> 32), x);
+	for(int k = 0; k < 3; k++) h->pending_shift[k] = unit_from_u32(x[k]) * (h->box[k] / h->n_side[k]);
+	if(ensure_cells_valid(h)) return 1;
+	const SimConst sc_new = make_const(h, h->box, h->pending_shift);
+	const int tp = (h->cp + 2) % 3, to = h->co ^ 1;
+	prof_begin(h);
+	const int nl = launch_slab_classify(sc_new, h->layer_slots[1], h->layer_slots[4], h->x0, h->x1 - h->x0, view(h, h->cp, h->co), view(h, tp, to),
+			h->outbox[0], h->outbox[1], h->cap_records, h->d_slab_counts, h->stream);
+	prof_end(h, PP_K_CELLS, nl);
+	int counts[4];
+	CUDA_OK(h, cudaMemcpyAsync(counts, h->d_slab_counts, sizeof(counts), cudaMemcpyDeviceToHost, h->stream));
+	CUDA_OK(h, cudaStreamSynchronize(h->stream));
+	if(counts[3]) return fail(h, "%d particles moved by more than one x layer at a grid shift", counts[3]);
+	if(counts[1] > h->cap_records || counts[2] > h->cap_records) return fail(h, "slab outbox overflow (%d, %d records, capacity %d)", counts[1], counts[2], h->cap_records);
+	h->keep_count = counts[0];
+	h->out_count[0] = counts[1];
+	h->out_count[1] = counts[2];
+	h->in_count[0] = h->in_count[1] = 0;
+	h->slab_pending = true;
+	*exchange = 1;
+	return 0;
+}
+
+int pp_slab_outbox(pp_handle *h, int side, void **dev, int *count) {
+	if(h == nullptr || side < 0 || side > 1) return 1;
+	if(dev) *dev = h->outbox[side];
+	if(count) *count = h->out_count[side];
+	return 0;
+}
+
+int pp_slab_inbox(pp_handle *h, int side, int count, void **dev) {
+	if(h == nullptr || side < 0 || side > 1) return 1;
+	if(count < 0 || count > h->cap_records) return fail(h, "slab inbox overflow (%d records, capacity %d)", count, h->cap_records);
+	h->in_count[side] = count;
+	if(dev) *dev = h->inbox[side];
+	return 0;
+}
+
+int pp_slab_sweep_rebuild(pp_handle *h) {
+	if(h == nullptr) return 1;
+	if(!h->slab_pending) return fail(h, "pp_slab_sweep_rebuild without a pending exchange");
+	const int tp = (h->cp + 2) % 3, to = h->co ^ 1;
+	const int n_new = h->keep_count + h->in_count[0] + h->in_count[1];
+	if((size_t) n_new > h->cap_N) return fail(h, "slab: %d local particles exceed the capacity %zu", n_new, h->cap_N);
+	launch_slab_unpack(h->in_count[0], h->inbox[0], h->keep_count, view(h, tp, to), h->stream);
+	launch_slab_unpack(h->in_count[1], h->inbox[1], h->keep_count + h->in_count[0], view(h, tp, to), h->stream);
+	// sort the merged set on the new grid; the previous current buffers are free to be the destination
+	h->N = n_new;
+	memcpy(h->shift, h->pending_shift, sizeof(h->shift));
+	const SimConst sc = make_const(h, h->box, h->shift);
+	prof_begin(h);
+	const int nl = launch_cell_build(sc, h->cb, view(h, tp, to), view(h, h->cp, h->co), h->slot_of, h->stream);
+	prof_end(h, PP_K_CELLS, nl);
+	CUDA_OK(h, cudaGetLastError());
+	h->cells_valid = true;
+	h->sweep_grid = true;
+	h->slab_pending = false;
+	if(slab_after_sort(h)) return 1;
+	if(h->N != n_new) return fail(h, "slab: %d of %d particles fell outside the held layers after the exchange", n_new - h->N, n_new);
+	return 0;
+}
+
+int pp_slab_pass_block(pp_handle *h, int cx) {
+	if(h == nullptr || cx < 0 || cx > 1) return 1;
+	if(h->slab_world <= 1) return fail(h, "pp_slab_pass_block without a slab decomposition");
+	if(!h->sweep_grid || !h->cells_valid) return fail(h, "pp_slab_pass_block before pp_slab_sweep_begin / _rebuild");
+	const SimConst sc = make_const(h, h->box, h->shift);
+	if(cx == 0) {
+		prof_begin(h);
+		const int nr = launch_proposals_for_sweep(sc, h->cb, h->d_proposals, h->stream);
+		prof_end(h, PP_K_RNG, nr);
+	}
+	int lanes = h->prm.lanes_per_cell;
+	if(lanes == 0 || lanes == 1) lanes = (h->N >= 400000) ? 8 : 16;
+	prof_begin(h);
+	int nl = 0;
+	for(int sub = 0; sub < 4; sub++) {
+		const int colour = cx | (((sub >> 1) & 1) << 1) | ((sub & 1) << 2); // same order as pp_sweep: passes 4 cx .. 4 cx + 3
+		nl += launch_sweep_pass(sc, colour, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
+	}
+	prof_end(h, PP_K_SWEEP, nl);
+	CUDA_OK(h, cudaGetLastError());
+	return 0;
+}
+
+int pp_slab_halo(pp_handle *h, int side, int recv, void **pos, void **ori, void **posf, int *count) {
+	if(h == nullptr || side < 0 || side > 1) return 1;
+	if(h->slab_world <= 1 || !h->cells_valid) return fail(h, "pp_slab_halo: no valid slab layout");
+	// send: my first (side 0) / last (side 1) owned layer; recv: my left (side 0) / right (side 1) halo layer
+	int b, e;
+	if(recv) {
+		b = side == 0 ? h->layer_slots[0] : h->layer_slots[4];
+		e = side == 0 ? h->layer_slots[1] : h->layer_slots[5];
+	}
+	else {
+		b = side == 0 ? h->layer_slots[1] : h->layer_slots[3];
+		e = side == 0 ? h->layer_slots[2] : h->layer_slots[4];
+	}
+	if(pos) *pos = h->pos[h->cp] + b;
+	if(ori) *ori = h->ori[h->co] + 9ll * b;
+	if(posf) *posf = h->cb.posf + b;
+	if(count) *count = e - b;
+	return 0;
+}
+
+int pp_slab_sweep_end(pp_handle *h) {
+	if(h == nullptr) return 1;
+	h->step++;
+	return 0;
+}
+
+int pp_slab_download(pp_handle *h, int *n_owned, int *ids, double *r, double *orient) {
+	if(h == nullptr) return 1;
+	if(h->slab_world <= 1) return fail(h, "pp_slab_download without a slab decomposition");
+	if(ensure_cells_valid(h)) return 1;
+	const int b = h->layer_slots[1], e = h->layer_slots[4], n = e - b;
+	if(n_owned) *n_owned = n;
+	if(ids == nullptr || n == 0) return 0;
+	int *d_ids = h->cb.cell_of; // scratch
+	launch_slab_download(b, e, view(h, h->cp, h->co), d_ids, h->d_stage_r, h->d_stage_o, h->stream);
+	CUDA_OK(h, cudaMemcpyAsync(ids, d_ids, sizeof(int) * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+	CUDA_OK(h, cudaMemcpyAsync(r, h->d_stage_r, sizeof(double) * 3 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+	CUDA_OK(h, cudaMemcpyAsync(orient, h->d_stage_o, sizeof(double) * 9 * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+	CUDA_OK(h, cudaStreamSynchronize(h->stream));
 	return 0;
 }
 

@@ -33,8 +33,10 @@ __global__ void __launch_bounds__(kBondThreads) k_total_bonds(const __grid_const
 	const int nyz = sc.n_side[1] * sc.n_side[2];
 	for(int cell = blockIdx.x * kTiles + tile_in_block; cell < sc.n_cells; cell += gridDim.x * kTiles) {
 		const int first = cell_start[cell], last = cell_start[cell + 1];
-		if(first == last) continue;
 		const int ix = cell / nyz, iy = (cell - ix * nyz) / sc.n_side[2], iz = cell - ix * nyz - iy * sc.n_side[2];
+		// only owned layers; a pair across a slab boundary is counted by the engine on its left, because the
+		// right halo comes after every owned slot and the left halo before (slot_q > slot_p below)
+		if(first == last || ix < sc.own_lo || ix >= sc.own_hi) continue;
 		Neighbourhood &nb = s_nb[tile_in_block];
 		tile.sync();
 		const int total = build_neighbourhood<G>(tile, sc, cell_start, ix, iy, iz, nb);
@@ -99,8 +101,10 @@ __global__ void __launch_bounds__(kBondThreads) k_bond_counts(const __grid_const
 	const int nyz = sc.n_side[1] * sc.n_side[2];
 	for(int cell = blockIdx.x * kTiles + tile_in_block; cell < sc.n_cells; cell += gridDim.x * kTiles) {
 		const int first = cell_start[cell], last = cell_start[cell + 1];
-		if(first == last) continue;
 		const int ix = cell / nyz, iy = (cell - ix * nyz) / sc.n_side[2], iz = cell - ix * nyz - iy * sc.n_side[2];
+		// only owned layers; a pair across a slab boundary is counted by the engine on its left, because the
+		// right halo comes after every owned slot and the left halo before (slot_q > slot_p below)
+		if(first == last || ix < sc.own_lo || ix >= sc.own_hi) continue;
 		Neighbourhood &nb = s_nb[tile_in_block];
 		tile.sync();
 		const int total = build_neighbourhood<G>(tile, sc, cell_start, ix, iy, iz, nb);

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(256) k_cell_count(const __grid_constant__ SimC
 	if(i >= sc.N) return;
 	const double4 p = pos[i];
 	int ix, iy, iz;
-	const int c = cell_index(sc, p.x, p.y, p.z, ix, iy, iz);
+	int c = cell_index(sc, p.x, p.y, p.z, ix, iy, iz);
+	if(c < 0) c = sc.n_cells; // not in a layer held here (slab decomposition): parked in the trash cell, dropped after the sort
 	cell_of[i] = c;
 	atomicAdd(cell_count + c, 1);
 }
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(int N, const int *__restri
 __device__ __forceinline__ int work_bin(const SimConst &sc, int c, int n) {
 	const int nyz = sc.n_side[1] * sc.n_side[2];
 	const int ix = c / nyz, iy = (c - ix * nyz) / sc.n_side[2], iz = c - ix * nyz - iy * sc.n_side[2];
-	const int colour = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
+	const int colour = ((ix + sc.x_lo) & 1) | ((iy & 1) << 1) | ((iz & 1) << 2); // parity of the GLOBAL layer
 	const int bucket = n < kWorkBuckets ? n : kWorkBuckets;        // 1 .. kWorkBuckets
 	return colour * kWorkBuckets + (kWorkBuckets - bucket);           // big cells first
 }
@@ -121,6 +122,8 @@ __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimC
 	if(c >= sc.n_cells) return;
 	const int b = cell_start[c], e = cell_start[c + 1];
 	if(e == b) return;
+	const int layer = c / (sc.n_side[1] * sc.n_side[2]);
+	const bool owned = layer >= sc.own_lo && layer < sc.own_hi;
 	for(int a = b + 1; a < e; a++) {
 		const int src = perm[a];
 		const int key = pid_src[src];
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimC
 		}
 		perm[k + 1] = src;
 	}
-	atomicAdd(bin_count + work_bin(sc, c, e - b), 1);
+	if(owned) atomicAdd(bin_count + work_bin(sc, c, e - b), 1); // halo cells are never moved here
 }
 
 // one warp: exclusive scan of the 8 * kWorkBuckets bins; work_start[colour] marks the colour boundaries
@@ -155,7 +158,8 @@ __global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ Si
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if(c >= sc.n_cells) return;
 	const int n = cell_start[c + 1] - cell_start[c];
-	if(n == 0) return;
+	const int layer = c / (sc.n_side[1] * sc.n_side[2]);
+	if(n == 0 || layer < sc.own_lo || layer >= sc.own_hi) return;
 	const int bin = work_bin(sc, c, n);
 	work[bin_start[bin] + atomicAdd(bin_fill + bin, 1)] = c;
 }
@@ -185,7 +189,8 @@ __global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int
 
 // ---------------------------------------------------------------------------------------------
 int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, cudaStream_t st) {
-	const int N = sc.N, nc = sc.n_cells;
+	const int N = sc.N;
+	const int nc = sc.n_cells + 1; // + the trash cell that collects particles outside the held layers
 	cudaMemsetAsync(cb.bins, 0, sizeof(int) * kBinInts, st);
 	if(N == 0) {
 		cudaMemsetAsync(cb.cell_start, 0, sizeof(int) * (size_t) (nc + 1), st);
@@ -193,7 +198,7 @@ int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView
 	}
 	cudaMemsetAsync(cb.cell_count, 0, sizeof(int) * (size_t) nc, st);
 	cudaMemsetAsync(cb.cell_fill, 0, sizeof(int) * (size_t) nc, st);
-	const int nb = (N + 255) / 256, ncb = (nc + 255) / 256;
+	const int nb = (N + 255) / 256, ncb = (sc.n_cells + 255) / 256;
 	k_cell_count<<<nb, 256, 0, st>>>(sc, src.pos, cb.cell_of, cb.cell_count);
 	const int n_tiles = (nc + kScanTile - 1) / kScanTile;
 	k_scan_tiles<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_count, cb.cell_start, cb.tile_sums, nc);

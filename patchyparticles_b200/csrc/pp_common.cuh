@@ -26,9 +26,16 @@ struct SimConst {
 	double cell_w[3];     // box / n_side
 	double inv_box[3];    // 1 / box (host-rounded)
 	double inv_w[3];      // n_side * inv_box
-	int n_side[3];        // even cell grid
-	int n_cells;
+	int n_side[3];        // even cell grid (global)
+	int n_cells;          // cells held by this engine: nxl * n_side[1] * n_side[2]
 	int N;
+	// x-slab decomposition: this engine holds the x layers x_lo .. x_lo + nxl - 1 (mod n_side[0]) of the global
+	// grid; with slab != 0 the first and the last of them are halo layers owned by the neighbouring engines
+	int nxl;              // layers held (n_side[0] when slab == 0)
+	int x_lo;             // global index of local layer 0
+	int slab;
+	int own_lo, own_hi;   // local layers [own_lo, own_hi) are owned (moved, counted) by this engine
+	int pad1;
 	double sqr_rcut;      // (1 + delta)^2                               system.c:86
 	double cosmax;        // KF_cosmax
 	double cos2_lo, cos2_hi; // cosmax^2 (1 -+ 1e-11): guard band of the division-free patch test
@@ -87,11 +94,22 @@ __device__ __forceinline__ int cell_coord(double r, double shift, double inv_box
 	return c < n_side ? c : n_side - 1;
 }
 
+// Linear index in this engine's cell array; ix is the LOCAL layer.  -1: the position lies in a layer this
+// engine does not hold (only possible with a slab decomposition).
 __device__ __forceinline__ int cell_index(const SimConst &sc, double x, double y, double z, int &ix, int &iy, int &iz) {
-	ix = cell_coord(x, sc.shift[0], sc.inv_box[0], sc.n_side[0]);
+	ix = cell_coord(x, sc.shift[0], sc.inv_box[0], sc.n_side[0]) - sc.x_lo;
+	ix += (ix < 0) ? sc.n_side[0] : 0;
 	iy = cell_coord(y, sc.shift[1], sc.inv_box[1], sc.n_side[1]);
 	iz = cell_coord(z, sc.shift[2], sc.inv_box[2], sc.n_side[2]);
+	if(ix >= sc.nxl) return -1;
 	return (ix * sc.n_side[1] + iy) * sc.n_side[2] + iz;
+}
+
+// index of a local cell in the GLOBAL grid: the key of its random streams, identical on every decomposition
+__device__ __forceinline__ int global_cell(const SimConst &sc, int ix, int iy, int iz) {
+	int gx = ix + sc.x_lo;
+	gx -= (gx >= sc.n_side[0]) ? sc.n_side[0] : 0;
+	return (gx * sc.n_side[1] + iy) * sc.n_side[2] + iz;
 }
 
 // FP32 shadow of a position: offset inside its cell along x, y, z and the cell's z index.  Only the
@@ -301,11 +319,12 @@ __device__ __forceinline__ int build_neighbourhood(const cg::thread_block_tile<G
 		int cnt = 0, first = 0;
 		if(l < 27) {
 			const int dx = l / 9 - 1, dy = (l / 3) % 3 - 1, dz = l % 3 - 1;
-			const bool dup = (sc.n_side[0] == 2 && dx < 0) || (sc.n_side[1] == 2 && dy < 0) || (sc.n_side[2] == 2 && dz < 0);
+			bool dup = (!sc.slab && sc.nxl == 2 && dx < 0) || (sc.n_side[1] == 2 && dy < 0) || (sc.n_side[2] == 2 && dz < 0);
+			int cx = ix + dx, cy = iy + dy, cz = iz + dz;
+			if(sc.slab) dup |= (cx < 0 || cx >= sc.nxl); // beyond the halo: never needed by an owned cell
 			if(!dup) {
-				int cx = ix + dx, cy = iy + dy, cz = iz + dz;
-				cx += (cx < 0) ? sc.n_side[0] : 0;
-				cx -= (cx >= sc.n_side[0]) ? sc.n_side[0] : 0;
+				cx += (cx < 0) ? sc.nxl : 0;
+				cx -= (cx >= sc.nxl) ? sc.nxl : 0;
 				cy += (cy < 0) ? sc.n_side[1] : 0;
 				cy -= (cy >= sc.n_side[1]) ? sc.n_side[1] : 0;
 				cz += (cz < 0) ? sc.n_side[2] : 0;

@@ -81,6 +81,12 @@ int launch_commit(int slot, const double *disp3, const double *orient9, double4 
 // K6: Gram-Schmidt on every orientation matrix
 int launch_orthonormalise(int N, double *ori, cudaStream_t st);
 
+// x-slab decomposition (pp_slab.cu)
+int launch_slab_classify(const SimConst &sc_new, int slot_begin, int slot_end, int x0, int n_owned_layers, const StateView &cur, const StateView &keep,
+		double *out_left, double *out_right, int cap_records, int *counts, cudaStream_t st);
+int launch_slab_unpack(int n, const double *records, int offset, const StateView &dst, cudaStream_t st);
+int launch_slab_download(int slot_begin, int slot_end, const StateView &cur, int *ids, double *r, double *orient, cudaStream_t st);
+
 // upload / download helpers (caller order <-> slot order)
 int launch_pack_state(int N, const double *r, const double *orient, double4 *pos, double *ori, int *pid, cudaStream_t st);
 int launch_unpack_state(int N, const double4 *pos, const double *ori, const int *pid, double *r, double *orient, cudaStream_t st);

@@ -1,0 +1,123 @@
+// pp_slab.cu -- kernels of the x-slab decomposition.
+//
+// Each engine (one per GPU) holds the particles of a contiguous range of x layers of the global
+// cell grid plus one halo layer on each side.  Cells are stored x-major, so a layer is a contiguous
+// range of particle slots: the in-period halo refresh is a plain copy of three array slices
+// (positions, orientations, FP32 shadow) and needs no kernel.  The kernels here serve the start of
+// a shift period, when the grid origin moves and particles change owner:
+//   k_slab_classify  walks the owned particles with the NEW grid and splits them into "kept" (new
+//                    layer still held here, as owner or as halo copy), "to the left neighbour"
+//                    (its new last owned layer or its new right halo) and "to the right
+//                    neighbour"; boundary-layer particles and migrants are both kept and sent;
+//   k_slab_unpack    appends the records received from a neighbour to the kept particles;
+//   k_slab_download  compacts the owned particles for output.
+// A record is 13 doubles: x, y, z, id, orientation[9].
+#include "pp_kernels.cuh"
+
+namespace pp {
+
+__global__ void __launch_bounds__(256) k_slab_classify(const __grid_constant__ SimConst sc_new, int slot_begin, int slot_end, int x0, int n_owned_layers,
+		const double4 *__restrict__ pos, const double *__restrict__ ori, const int *__restrict__ pid, double4 *__restrict__ keep_pos,
+		double *__restrict__ keep_ori, int *__restrict__ keep_pid, double *__restrict__ out_left, double *__restrict__ out_right, int cap_records,
+		int *__restrict__ counts /* keep, left, right, error */) {
+	const int s = slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if(s >= slot_end) return;
+	const double4 p = pos[s];
+	const int nx = sc_new.n_side[0];
+	int rel = cell_coord(p.x, sc_new.shift[0], sc_new.inv_box[0], nx) - x0; // new global layer relative to the first owned one
+	rel += (rel < 0) ? nx : 0;
+	// kept: everything that lies in a layer held here under the new grid -- the owned layers and the two halo
+	// layers (a particle migrating to a neighbour stays behind as a halo copy)
+	const bool keep = (rel <= n_owned_layers) || (rel == nx - 1);
+	const bool left = (rel == 0) || (rel == nx - 1);
+	const bool right = (rel == n_owned_layers - 1) || (rel == n_owned_layers);
+	if(!keep && !left && !right) {
+		atomicAdd(counts + 3, 1); // moved by more than one layer: impossible while the shift changes by less than a cell
+		return;
+	}
+	double m[9];
+#pragma unroll
+	for(int k = 0; k < 9; k++) m[k] = ori[9ll * s + k];
+	if(keep) {
+		const int d = atomicAdd(counts + 0, 1);
+		keep_pos[d] = p;
+		keep_pid[d] = pid[s];
+#pragma unroll
+		for(int k = 0; k < 9; k++) keep_ori[9ll * d + k] = m[k];
+	}
+	if(left) {
+		const int d = atomicAdd(counts + 1, 1);
+		if(d < cap_records) {
+			double *rec = out_left + 13ll * d;
+			rec[0] = p.x;
+			rec[1] = p.y;
+			rec[2] = p.z;
+			rec[3] = p.w;
+#pragma unroll
+			for(int k = 0; k < 9; k++) rec[4 + k] = m[k];
+		}
+	}
+	if(right) {
+		const int d = atomicAdd(counts + 2, 1);
+		if(d < cap_records) {
+			double *rec = out_right + 13ll * d;
+			rec[0] = p.x;
+			rec[1] = p.y;
+			rec[2] = p.z;
+			rec[3] = p.w;
+#pragma unroll
+			for(int k = 0; k < 9; k++) rec[4 + k] = m[k];
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_slab_unpack(int n, const double *__restrict__ records, int offset, double4 *__restrict__ pos,
+		double *__restrict__ ori, int *__restrict__ pid) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const double *rec = records + 13ll * i;
+	const int d = offset + i;
+	pos[d] = make_double4(rec[0], rec[1], rec[2], rec[3]);
+	pid[d] = (int) rec[3];
+#pragma unroll
+	for(int k = 0; k < 9; k++) ori[9ll * d + k] = rec[4 + k];
+}
+
+__global__ void __launch_bounds__(256) k_slab_download(int slot_begin, int slot_end, const double4 *__restrict__ pos, const double *__restrict__ ori,
+		const int *__restrict__ pid, int *__restrict__ ids, double *__restrict__ r, double *__restrict__ orient) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int s = slot_begin + i;
+	if(s >= slot_end) return;
+	const double4 p = pos[s];
+	ids[i] = pid[s];
+	r[3ll * i] = p.x;
+	r[3ll * i + 1] = p.y;
+	r[3ll * i + 2] = p.z;
+#pragma unroll
+	for(int k = 0; k < 9; k++) orient[9ll * i + k] = ori[9ll * s + k];
+}
+
+int launch_slab_classify(const SimConst &sc_new, int slot_begin, int slot_end, int x0, int n_owned_layers, const StateView &cur, const StateView &keep,
+		double *out_left, double *out_right, int cap_records, int *counts, cudaStream_t st) {
+	cudaMemsetAsync(counts, 0, 4 * sizeof(int), st);
+	const int n = slot_end - slot_begin;
+	if(n <= 0) return 0;
+	k_slab_classify<<<(n + 255) / 256, 256, 0, st>>>(sc_new, slot_begin, slot_end, x0, n_owned_layers, cur.pos, cur.ori, cur.pid, keep.pos, keep.ori,
+			keep.pid, out_left, out_right, cap_records, counts);
+	return 1;
+}
+
+int launch_slab_unpack(int n, const double *records, int offset, const StateView &dst, cudaStream_t st) {
+	if(n <= 0) return 0;
+	k_slab_unpack<<<(n + 255) / 256, 256, 0, st>>>(n, records, offset, dst.pos, dst.ori, dst.pid);
+	return 1;
+}
+
+int launch_slab_download(int slot_begin, int slot_end, const StateView &cur, int *ids, double *r, double *orient, cudaStream_t st) {
+	const int n = slot_end - slot_begin;
+	if(n <= 0) return 0;
+	k_slab_download<<<(n + 255) / 256, 256, 0, st>>>(slot_begin, slot_end, cur.pos, cur.ori, cur.pid, ids, r, orient);
+	return 1;
+}
+
+} // namespace pp

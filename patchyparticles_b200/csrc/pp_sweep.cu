@@ -40,10 +40,14 @@ __global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ 
 		const int *__restrict__ cell_sorted, Proposal *__restrict__ out) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= sc.N) return;
-	const int cell = cell_sorted[i];
-	const int first = cell_start[cell];
-	const int n_here = cell_start[cell + 1] - first;
+	const int lcell = cell_sorted[i];
+	const int nyz = sc.n_side[1] * sc.n_side[2];
+	const int lx = lcell / nyz, ly = (lcell - lx * nyz) / sc.n_side[2], lz = lcell - lx * nyz - ly * sc.n_side[2];
+	if(lx < sc.own_lo || lx >= sc.own_hi) return; // halo particle: moved by its owner
+	const int first = cell_start[lcell];
+	const int n_here = cell_start[lcell + 1] - first;
 	const int t = i - first;
+	const int cell = global_cell(sc, lx, ly, lz); // random streams are keyed by the global cell
 	const uint4 x = philox4x32((uint32_t) cell, (uint32_t) t, sc.sweep_lo, sc.sweep_hi8 | 0u, sc.seed_lo, sc.seed_hi);
 	const uint4 y = philox4x32((uint32_t) cell, (uint32_t) t, sc.sweep_lo, sc.sweep_hi8 | 1u, sc.seed_lo, sc.seed_hi);
 	Proposal pr;
@@ -341,7 +345,7 @@ static int launch_pass_g(const SimConst &sc, int colour, const CellBuffers &cb, 
 	constexpr int kThreads = sweep_threads<G>();
 	// the number of non-empty cells of this colour lives on the device (work_start); size the grid for
 	// the worst case (every active cell occupied, at most one cell per particle) and let surplus tiles exit
-	long long n_active = (long long) (sc.n_side[0] / 2) * (sc.n_side[1] / 2) * (sc.n_side[2] / 2);
+	long long n_active = (long long) (sc.nxl / 2 + 1) * (sc.n_side[1] / 2) * (sc.n_side[2] / 2);
 	if(n_active > sc.N) n_active = sc.N;
 	const int tiles_per_block = kThreads / G;
 	long long blocks = (n_active + tiles_per_block - 1) / tiles_per_block;

@@ -51,7 +51,9 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy", "pp_last_error", "pp_upload",
                "pp_download", "pp_total_bonds", "pp_bond_counts", "pp_sweep", "pp_sync", "pp_get_observables",
                "pp_check_energy", "pp_eval_proposals", "pp_volume_move", "pp_Lx_move", "pp_set_stream",
-               "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats"]
+               "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats", "pp_slab_setup", "pp_slab_range",
+               "pp_slab_sweep_begin", "pp_slab_outbox", "pp_slab_inbox", "pp_slab_sweep_rebuild", "pp_slab_pass_block",
+               "pp_slab_halo", "pp_slab_sweep_end", "pp_slab_download"]
 
 
 def load_library():
@@ -86,6 +88,17 @@ def load_library():
     L.pp_set_profiling.argtypes = [H, C.c_int]
     L.pp_kernel_stats.argtypes = [H, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     L.pp_reset_kernel_stats.argtypes = [H]
+    PI, PV = C.POINTER(C.c_int), C.POINTER(C.c_void_p)
+    L.pp_slab_setup.argtypes = [H, C.c_int, C.c_int]
+    L.pp_slab_range.argtypes = [H, PI, PI, PI, PI]
+    L.pp_slab_sweep_begin.argtypes = [H, PI]
+    L.pp_slab_outbox.argtypes = [H, C.c_int, PV, PI]
+    L.pp_slab_inbox.argtypes = [H, C.c_int, C.c_int, PV]
+    L.pp_slab_sweep_rebuild.argtypes = [H]
+    L.pp_slab_pass_block.argtypes = [H, C.c_int]
+    L.pp_slab_halo.argtypes = [H, C.c_int, C.c_int, PV, PV, PV, PI]
+    L.pp_slab_sweep_end.argtypes = [H]
+    L.pp_slab_download.argtypes = [H, PI, _ip, _dp, _dp]
     _lib = L
     return L
 
@@ -202,6 +215,54 @@ class Engine:
         a = C.c_int(0)
         self._check(self.L.pp_Lx_move(self.h, u_lx, u_acc, C.byref(a)))
         return int(a.value)
+
+    # ---- x-slab decomposition hooks (see slab.py) ------------------------------------------------
+    def slab_setup(self, rank, world):
+        self._check(self.L.pp_slab_setup(self.h, rank, world))
+
+    def slab_range(self):
+        v = [C.c_int(0) for _ in range(4)]
+        self._check(self.L.pp_slab_range(self.h, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)  # x0, x1, nx, n_local
+
+    def slab_sweep_begin(self):
+        ex = C.c_int(0)
+        self._check(self.L.pp_slab_sweep_begin(self.h, C.byref(ex)))
+        return bool(ex.value)
+
+    def slab_outbox(self, side):
+        ptr, n = C.c_void_p(), C.c_int(0)
+        self._check(self.L.pp_slab_outbox(self.h, side, C.byref(ptr), C.byref(n)))
+        return ptr.value, int(n.value)
+
+    def slab_inbox(self, side, count):
+        ptr = C.c_void_p()
+        self._check(self.L.pp_slab_inbox(self.h, side, int(count), C.byref(ptr)))
+        return ptr.value
+
+    def slab_sweep_rebuild(self):
+        self._check(self.L.pp_slab_sweep_rebuild(self.h))
+
+    def slab_pass_block(self, cx):
+        self._check(self.L.pp_slab_pass_block(self.h, cx))
+
+    def slab_halo(self, side, recv):
+        pos, ori, posf, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int(0)
+        self._check(self.L.pp_slab_halo(self.h, side, int(recv), C.byref(pos), C.byref(ori), C.byref(posf), C.byref(n)))
+        return pos.value, ori.value, posf.value, int(n.value)
+
+    def slab_sweep_end(self):
+        self._check(self.L.pp_slab_sweep_end(self.h))
+
+    def slab_download(self):
+        n = C.c_int(0)
+        cap = max(self.N, 1)
+        ids = np.zeros(cap, dtype=np.int32)
+        r = np.zeros((cap, 3))
+        m = np.zeros((cap, 9))
+        self._check(self.L.pp_slab_download(self.h, C.byref(n), ids, r, m))
+        k = int(n.value)
+        return ids[:k], r[:k], m[:k].reshape(-1, 3, 3)
 
     # ---- measurement plumbing --------------------------------------------------------------
     def set_stream(self, cuda_stream):

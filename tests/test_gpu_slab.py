@@ -1,0 +1,27 @@
+"""Multi-GPU: the x-slab decomposition against the single-GPU engine (needs >= 2 GPUs; run with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_slab.py -m gpu`)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("world,N,rho,sweeps", [(2, 20000, 0.5, 9), (2, 3000, 0.3, 13), (4, 40000, 0.55, 9), (8, 120000, 0.5, 5)])
+def test_slab_matches_single_gpu(world, N, rho, sweeps):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "slab_check.py"), str(N), str(rho), str(sweeps)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(p.stdout[-3000:])
+    assert p.returncode == 0, p.stderr[-3000:]
