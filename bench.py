@@ -42,6 +42,8 @@ SWEEP_BYTES_PER_ATTEMPT = 64   # state read once + writt
 CELLS_BYTES_PER_PARTICLE = 72
 BONDS_BYTES_PER_PARTICLE = 32
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+# dram__bytes_read.sum + dram__bytes_write.sum per k_sweep_pass launch from the committed ncu captures (profiles/)
+SWEEP_TRAFFIC_BYTES = {}
 
 
 def workload_name(w):
@@ -104,10 +106,11 @@ def time_reference(w, sweeps):
     if rrr is None:
         # no generator output (large N): write our synthetic configuration as .rrr
         import patchyparticles_b200 as pkg
+        import _oracle  # test-only C writer (output.c:302-317 format); allowed in the reference arm
         box, r, m = pkg.random_fluid(N, rho, seed=1)
         rrr = os.path.join(tempfile.gettempdir(), f"pp_synth_{N}_{rho}.rrr")
         if not os.path.exists(rrr):
-            pkg.write_rrr(rrr, 0, box, r, m)
+            _oracle.write_rrr(rrr, 0, box, r, m.reshape(-1, 9))
     d = tempfile.mkdtemp(prefix="ppref_")
     try:
         kind_flags = None
@@ -134,15 +137,14 @@ def time_reference(w, sweeps):
 
 def reference_sample_sweeps(w, budget_s=15.0):
     N = WORKLOADS[w][0]
-    est = N / 4.0e5  # ~4e5 attempts/s/core measured at survey time
+    est = N / (4.0e5 if N < 500000 else 1.5e5)  # attempts/s/core measured at survey time (cache-bound at 4M)
     return max(1, int(budget_s / est))
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    w = args.workload if args.workload != "auto" else "64k"
     N = WORKLOADS[w][0]
     sweeps = max(1, min(args.steps, reference_sample_sweeps(w, 40.0)))
     res = time_reference(w, sweeps)
@@ -152,8 +154,8 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "MC roto-translation attempts/sec", "value": res["value"], "unit": "attempts/s",
         "n_gpus": args.gpus, "steps": sweeps, "warmup": 0, "ms_per_step": 1e3 * res["seconds"] / sweeps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(w), "N": N},
+        "higher_is_better": True, "scaling": "strong" if WORKLOADS[w][0] > 500000 else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_name(w), "N_total": N},
         "cpu_baseline": {"value": res["value"], "unit": "attempts/s", "cores": 1, "kind": "reference",
                          "sample": f"{sweeps} MC steps of the unmodified reference ({res['flags']}), wall(steps) - wall(0 steps); "
                                    "the reference is single-threaded"},
@@ -224,19 +226,73 @@ def measured_peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+class Arm:
+    """The engine under test: one Engine (world == 1 or independent replicas) or one SlabEngine rank."""
+
+    def __init__(self, pkg, args, w, rank, local_rank, world, sharded):
+        import torch
+        N, rho, T = WORKLOADS[w]
+        params = dict(temperature=T, kf_delta=KF_DELTA, kf_cosmax=KF_COSMAX, disp_max=DISP_MAX, theta_max=THETA_MAX,
+                      lanes_per_cell=args.lanes)
+        self.sharded = sharded
+        if sharded:
+            from patchyparticles_b200.slab import SlabEngine
+            self.drv = SlabEngine(rank, world, local_rank, seed=SEED, **params)
+            self.eng = self.drv.eng
+        else:
+            self.eng = pkg.Engine(seed=SEED + rank, device=local_rank, **params)
+            self.eng.set_stream(torch.cuda.current_stream().cuda_stream)
+            self.drv = self.eng
+
+    def upload(self, box, r, m):
+        self.drv.upload(box, r, m)
+
+    def total_bonds(self):
+        return self.drv.total_bonds()
+
+    def sweep(self, n, sync=False):
+        self.drv.sweep(n, sync=sync)
+
+    def pair_checks(self):
+        o = self.drv.observables()
+        return o["pair_checks"] if self.sharded else o.pair_checks
+
+    def result_readback(self):
+        """D2H of the step's result: the running energy and the counters."""
+        return self.drv.observables()
+
+    def check_energy(self):
+        return self.drv.check_energy()
+
+    def cells(self):
+        return list(self.eng.observables().n_side)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas of the 1-GPU workload instead of one sharded system")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-steps", type=int, default=None)
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # N = 1: BASELINE.json configs[1] (N = 65536).  N > 1: configs[3], one N = 4M system sharded into x slabs (strong scaling)
+    sharded = world > 1 and not args.replicas
+    w = args.workload if args.workload != "auto" else ("4M" if sharded else "64k")
+    big = WORKLOADS[w][0] > 500000
+    if args.steps is None:
+        args.steps = 200 if big else 2000
+    if args.warmup is None:
+        args.warmup = 10 if big else 50
+    if args.e2e_steps is None:
+        args.e2e_steps = 5 if big else 200
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, w)
 
     import numpy as np
     import torch
@@ -244,7 +300,6 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -258,23 +313,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    w = args.workload if args.workload != "auto" else "64k"
     N, rho, T = WORKLOADS[w]
     K, W = args.steps, max(args.warmup, 3)
     box, r, m, data_desc, _ = make_configuration(w)
-
-    eng = pkg.Engine(temperature=T, kf_delta=KF_DELTA, kf_cosmax=KF_COSMAX, disp_max=DISP_MAX, theta_max=THETA_MAX,
-                     seed=SEED + rank, device=local_rank, lanes_per_cell=args.lanes)
     stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
-    eng.upload(box, r, m)
-    bonds0, ov0 = eng.total_bonds()
+    arm = Arm(pkg, args, w, rank, local_rank, world, sharded)
+    eng = arm.eng
+    arm.upload(box, r, m)
+    bonds0, ov0 = arm.total_bonds()
     assert ov0 == 0, "initial configuration overlaps"
+    n_systems = 1 if sharded else world          # independent systems in flight
+    attempts_per_step = float(N) * n_systems      # whole-job attempts per step
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # ---- warm-up ----------------------------------------------------------------------------
-    eng.sweep(W, sync=True)
+    arm.sweep(W, sync=True)
     flush.zero_()
     barrier()
 
@@ -290,29 +344,25 @@ def main():
     for i in range(K):
         flush.zero_()
         starts[i].record(stream)
-        eng.sweep(1, sync=False)
+        arm.sweep(1)
         ends[i].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    step_ms = np.array([s_.elapsed_time(e_) for s_, e_ in zip(starts, ends)])
     launches_timed = sum(v[0] for v in eng.kernel_stats().values())
     total_ms = float(step_ms.sum())
 
     # ---- same K steps back to back without the flush (steady state of a real run) -----------------
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    checks0 = eng.observables().pair_checks
+    checks0 = arm.pair_checks()
     barrier()
     ev0.record(stream)
-    eng.sweep(K, sync=False)
+    arm.sweep(K)
     ev1.record(stream)
     barrier()
     warm_ms = ev0.elapsed_time(ev1)
-    pair_checks_per_s = (eng.observables().pair_checks - checks0) / (warm_ms * 1e-3)
+    pair_checks_per_s = (arm.pair_checks() - checks0) * (1 if sharded else world) / (warm_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
-
-    # invariant after the timed region: running energy == recount (MC_check_energy)
-    b_chk, ov_chk, ok = eng.check_energy()
-    assert ok, "energy check failed after the timed region"
 
     # ---- per-kernel timing for the roofline (CUDA events around each kernel class) -----------------
     eng.set_profiling(True)
@@ -320,40 +370,47 @@ def main():
     n_prof = min(K, 300)
     for i in range(n_prof):
         flush.zero_()
-        eng.sweep(1, sync=False)
-    eng.total_bonds()
+        arm.sweep(1)
+    arm.total_bonds()
     eng.sync()
     stats = eng.kernel_stats()
     eng.set_profiling(False)
+    n_local = eng.slab_range()[3] if sharded else N
     peak, peak_src = measured_peaks()
     sweep_launches, sweep_ms = stats["sweep"]
     per_launch_ms = sweep_ms / max(sweep_launches, 1)
-    bytes_per_launch = SWEEP_BYTES_PER_ATTEMPT * N / 8.0
+    n_owned = N / world if sharded else N
+    bytes_per_launch = SWEEP_BYTES_PER_ATTEMPT * n_owned / 8.0
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+    cell_builds = max(stats["cells"][0] // 10, 1)
     kernels = {
         "sweep_pass": {"launches": sweep_launches, "ms_per_launch": per_launch_ms, "alg_bytes_per_launch": bytes_per_launch, "GBps": achieved},
-        "cell_build": {"launches": stats["cells"][0], "ms_per_build": stats["cells"][1] / n_prof,
-                       "GBps": CELLS_BYTES_PER_PARTICLE * N / (stats["cells"][1] / n_prof * 1e-3) / 1e9},
+        "cell_build": {"launches": stats["cells"][0], "builds": cell_builds, "ms_per_build": stats["cells"][1] / cell_builds,
+                       "GBps": CELLS_BYTES_PER_PARTICLE * n_local / (stats["cells"][1] / cell_builds * 1e-3) / 1e9},
         "proposals": {"launches": stats["rng"][0], "ms_per_launch": stats["rng"][1] / max(stats["rng"][0], 1)},
         "bond_count": {"launches": stats["bonds"][0], "ms": stats["bonds"][1],
-                       "GBps": BONDS_BYTES_PER_PARTICLE * N / (max(stats["bonds"][1], 1e-9) * 1e-3) / 1e9},
+                       "GBps": BONDS_BYTES_PER_PARTICLE * n_owned / (max(stats["bonds"][1], 1e-9) * 1e-3) / 1e9},
     }
 
-    # ---- e2e through the C ABI with host buffers ---------------------------------------------
+    # invariant after the measured regions: running energy == recount (MC_check_energy)
+    b_chk, ov_chk, ok = arm.check_energy()
+    assert ok, "energy check failed after the timed region"
+
+    # ---- e2e through the public API with host buffers ---------------------------------------------
     r_pin = torch.from_numpy(np.ascontiguousarray(r)).pin_memory()
     m_pin = torch.from_numpy(np.ascontiguousarray(m.reshape(-1, 9))).pin_memory()
     r_host, m_host = r_pin.numpy(), m_pin.numpy()
     n_e2e = max(3, min(args.e2e_steps, K))
-    for i in range(3):
-        eng.upload(box, r_host, m_host)
-        eng.sweep(1, sync=False)
-        eng.observables()
+    for i in range(2):
+        arm.upload(box, r_host, m_host)
+        arm.sweep(1)
+        arm.result_readback()
     barrier()
     t0 = time.perf_counter()
     for i in range(n_e2e):
-        eng.upload(box, r_host, m_host)       # H2D of the step's input configuration + cell build
-        eng.sweep(1, sync=False)              # one MC step
-        obs = eng.observables()               # D2H of the step's result (energy change, counters)
+        arm.upload(box, r_host, m_host)       # H2D of the step's input configuration + cell build
+        arm.sweep(1)                          # one MC step
+        arm.result_readback()                 # D2H of the step's result (energy, counters)
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = int(r_host.nbytes + m_host.nbytes)
@@ -364,11 +421,10 @@ def main():
         t = torch.tensor([total_ms, warm_ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, warm_ms, e2e_s = [float(x) for x in t.tolist()]
-    attempts = float(K) * N * world
-    value = attempts / (total_ms * 1e-3)
+    value = K * attempts_per_step / (total_ms * 1e-3)
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = time_reference(w, reference_sample_sweeps(w, 15.0))
         if res is not None:
             cpu = {"value": res["value"], "unit": "attempts/s", "cores": 1, "kind": "reference",
@@ -376,25 +432,29 @@ def main():
                              "wall(steps) - wall(0 steps); single-threaded code"}
 
     if rank == 0:
-        o = eng.observables()
+        if sharded:
+            par = f"one system in {world} x-slabs, NCCL halo exchange (2 per sweep) + migration every shift period"
+        else:
+            par = "single GPU" if world == 1 else f"{world} independent replicas"
         line = {
             "metric": "MC roto-translation attempts/sec", "value": value, "unit": "attempts/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(w), "N_per_gpu": N, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+            "config": {"workload": workload_name(w), "N_total": int(N * n_systems), "parallelism": par,
                        "configuration": data_desc, "l2": "flushed between steps (256 MiB memset), per-step CUDA events on the launch stream",
-                       "lanes_per_cell": eng.params.lanes_per_cell or "default", "cells": list(o.n_side)},
-            "value_l2_warm": float(K) * N * world / (warm_ms * 1e-3),
+                       "lanes_per_cell": eng.params.lanes_per_cell or "auto", "cells": arm.cells()},
+            "value_l2_warm": K * attempts_per_step / (warm_ms * 1e-3),
             "wall_s_timed_region": t_wall,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": SWEEP_TRAFFIC_BYTES.get(w),
                          "kernel": "k_sweep_pass", "peak_source": peak_src + " (of measured)",
-                         "note": "algorithmic bytes = 64 B per attempted move (SURVEY 8d); the sweep is L2/latency bound, not HBM bound"},
+                         "note": "algorithmic bytes = 64 B per attempted move (SURVEY 8d); traffic = ncu dram bytes per launch (profiles/); "
+                                 "the sweep is latency / L2 bound, not HBM bound"},
             "kernels": kernels,
-            "pair_checks_per_s_l2_warm": pair_checks_per_s * world,
+            "pair_checks_per_s_l2_warm": pair_checks_per_s,
             "cpu_baseline": cpu,
-            "e2e": {"value": n_e2e * N * world / e2e_s, "unit": "attempts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "step": "pp_upload (pinned host configuration -> HBM, cell build) + pp_sweep(1) + pp_get_observables", "steps": n_e2e},
-            "gpu_launches": int(launches_timed),
+            "e2e": {"value": n_e2e * attempts_per_step / e2e_s, "unit": "attempts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "step": "pp_upload (pinned host configuration -> HBM, cell build) + one MC step + observables read-back", "steps": n_e2e},
+            "gpu_launches": int(launches_timed) * (world if sharded else 1),
             "clocks": clocks,
             "energy_check": {"bonds": b_chk, "ok": bool(ok)},
         }

@@ -5,7 +5,10 @@ density within 3 sigma of block-averaged error bars (BASELINE.json north_star).
 Parallel checkerboard dynamics is a different Markov chain from the reference's random sequential
 picks, so trajectories cannot be compared move by move; equilibrium averages must agree.  The state
 points are chosen where the reference equilibrates in a few thousand steps (SURVEY.md section 7,
-hard part 3): a T = 0.2 / cosmax = 0.92 fluid for NVT and a T = 0.3 fluid at P = 0.3 for NPT.
+hard part 3) AND decorrelates fast enough for block averages over ~10^4 steps to be honest error bars:
+a T = 0.3 / cosmax = 0.92 / rho = 0.4 bonded fluid for NVT (at T = 0.2 the energy autocorrelation
+time is thousands of steps and 10-block error bars are too small by ~2x; a 6 x 300000-step study of
+that algorithm at T = 0.3 is recorded in DESIGN.md) and a T = 0.3 fluid at P = 0.3 for NPT.
 """
 import os
 import subprocess
@@ -99,15 +102,15 @@ def test_host_output_formats(tmp_path):
 
 
 def test_nvt_statistics_vs_reference(tmp_path):
-    """<E>/N and roto-translation acceptance at equilibrium, N = 1000, rho = 0.3, T = 0.2, cosmax = 0.92."""
+    """<E>/N and roto-translation acceptance at equilibrium, N = 1000, rho = 0.4, T = 0.3, cosmax = 0.92."""
     need_binaries()
-    d_ref, d_gpu = make_case(tmp_path, 1000, 0.3, Steps=12000)
+    d_ref, d_gpu = make_case(tmp_path, 1000, 0.4, Steps=20000, Temperature=0.3, Print_every=10)
     run(REF_BIN, d_ref)
-    write_input(d_gpu / "input", **dict(Dynamics=0, Ensemble=0, Temperature=0.2, Steps=24000, Disp_max=0.2, Theta_max=0.3,
-                Initial_conditions_file=str(tmp_path / "generated.rrr"), Print_every=20, Save_every=100000000,
+    write_input(d_gpu / "input", **dict(Dynamics=0, Ensemble=0, Temperature=0.3, Steps=40000, Disp_max=0.2, Theta_max=0.3,
+                Initial_conditions_file=str(tmp_path / "generated.rrr"), Print_every=10, Save_every=100000000,
                 Configuration_folder=".", KF_delta=0.119, KF_cosmax=0.92, Seed=777, Log_file="none"))
     run(HOST_BIN, d_gpu)
-    discard = 4000
+    discard = 2000
     res = {}
     for tag, d in (("ref", d_ref), ("gpu", d_gpu)):
         e = load_cols(d / "energy.dat")
@@ -117,7 +120,7 @@ def test_nvt_statistics_vs_reference(tmp_path):
     (e_gpu, se_gpu), (a_gpu, sa_gpu) = res["gpu"]
     print(f"E/N ref {e_ref:.4f} +- {se_ref:.4f}   gpu {e_gpu:.4f} +- {se_gpu:.4f}")
     print(f"acc ref {a_ref:.4f} +- {sa_ref:.4f}   gpu {a_gpu:.4f} +- {sa_gpu:.4f}")
-    assert -0.9 < e_ref < -0.5  # the state point is the bonded fluid it is meant to be
+    assert -0.5 < e_ref < -0.15  # the state point is the bonded fluid it is meant to be
     assert abs(e_gpu - e_ref) < 3.0 * np.hypot(se_ref, se_gpu)
     assert abs(a_gpu - a_ref) < 3.0 * np.hypot(sa_ref, sa_gpu)
 

@@ -153,6 +153,49 @@ def test_sweep_restatement_invariants(oracle):
     assert np.array_equal(q.state()[0], p.state()[0]) and b2 == bonds
 
 
+def test_checkerboard_statistics_vs_reference(oracle, tmp_path):
+    """The checkerboard algorithm (serial restatement, same code path as the CUDA sweep) samples the same
+    ensemble as the reference's random sequential moves: <E>/N and the acceptance estimator agree within
+    3 sigma of block-averaged error bars.  N = 200, rho = 0.4, T = 0.3, cosmax = 0.92, 100000 steps each (first 20000 discarded)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import subprocess
+    subprocess.run([os.path.join(oracle.REF_DIR, "generator"), "200", "0.4"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    steps, every, discard = 100000, 10, 20000
+    oracle.write_input(str(tmp_path / "input"), str(tmp_path / "generated.rrr"), Temperature=0.3, Steps=steps, Disp_max=0.2, Theta_max=0.3,
+                       Print_every=every, KF_cosmax=0.92, Seed=11, Log_file="none")
+    subprocess.run([os.path.join(oracle.REF_DIR, "PatchyParticles"), "input"], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    e = np.loadtxt(tmp_path / "energy.dat")
+    a = np.loadtxt(tmp_path / "acceptance.dat")
+
+    def blocks(x, nb=20):
+        x = np.asarray(x)
+        n = (len(x) // nb) * nb
+        b = x[:n].reshape(nb, -1).mean(1)
+        return b.mean(), b.std(ddof=1) / np.sqrt(nb)
+
+    e_ref, se_ref = blocks(e[e[:, 0] >= discard, 1])
+    a_ref, sa_ref = blocks(a[a[:, 0] >= discard, 1])
+    _, box, r, m = oracle.read_rrr(str(tmp_path / "generated.rrr"))
+    p = oracle.PortSystem(box, r, m, kf_delta=0.119, kf_cosmax=0.92, temperature=0.3)
+    bonds, _ = p.total_bonds()
+    st, E, A, last = oracle.SweepStats(), [], [], (0, 0)
+    for s in range(steps):
+        bonds, st = p.sweep(5, s, 0.2, 0.3, bonds, st)
+        if s % every == 0 and s >= discard:
+            E.append(-bonds / len(r))
+            A.append((st.w_accepted - last[0]) / max(st.w_tries - last[1], 1))
+        if s % every == 0:
+            last = (st.w_accepted, st.w_tries)
+    e_port, se_port = blocks(E)
+    a_port, sa_port = blocks(A)
+    print(f"E/N ref {e_ref:.4f} +- {se_ref:.4f} port {e_port:.4f} +- {se_port:.4f}; acc ref {a_ref:.4f} +- {sa_ref:.4f} port {a_port:.4f} +- {sa_port:.4f}")
+    assert -0.4 < e_ref < -0.2
+    assert abs(e_port - e_ref) < 3 * np.hypot(se_ref, se_port)
+    assert abs(a_port - a_ref) < 3 * np.hypot(sa_ref, sa_port)
+
+
 def test_abi_exports_every_declared_symbol():
     """libpatchy_b200.so loads and exports every function include/pp_b200.h declares (no compute calls)."""
     import patchyparticles_b200 as pkg
