@@ -40,7 +40,7 @@ struct Proposal {
 	double dx, dy, dz;
 	double u_acc;
 	int pick;
-	int pad;
+	unsigned int wfix; // weight of the trial in the acceptance estimator, fixed point 2^-24
 };
 
 // one proposal of the K5 evaluator (device layout)

@@ -1,0 +1,90 @@
+// pp_trial_serial.cuh -- one roto-translation trial executed by a single thread, entirely in FP64 and
+// straight from global memory (MC.c:311-340 with the engine's confinement rule).  It is the
+// fallback of both sweep kernels for cells whose neighbourhood does not fit their staging area
+// (very dense packings, boxes with only two cells along an axis); same decisions as the staged
+// paths, only slower.
+#pragma once
+
+#include "pp_kernels.cuh"
+
+namespace pp {
+
+struct Tally {
+	unsigned int tries, acc, conf, ovl;
+	int dbonds;
+	unsigned long long wt, wa, checks;
+};
+
+__device__ __forceinline__ int wrap_cell(int c, int n) {
+	c += (c < 0) ? n : 0;
+	c -= (c >= n) ? n : 0;
+	return c;
+}
+
+static __device__ __noinline__ void trial_serial(const SimConst &sc, const int *__restrict__ cell_start, double4 *pos, double *ori, float4 *posf,
+		const Proposal *pr, int cell, int ix, int iy, int iz, int sp, Tally &tl) {
+	const int ny = sc.n_side[1], nz = sc.n_side[2];
+	const double4 p4 = pos[sp];
+	const Vec3 p_old = {p4.x, p4.y, p4.z};
+	const Vec3 p_new = {__dadd_rn(p4.x, pr->dx), __dadd_rn(p4.y, pr->dy), __dadd_rn(p4.z, pr->dz)};
+	int cx, cy, cz;
+	if(cell_index(sc, p_new.x, p_new.y, p_new.z, cx, cy, cz) != cell) { // would leave its cell
+		tl.conf++;
+		return;
+	}
+	const unsigned long long Wfix = (unsigned long long) pr->wfix;
+	tl.wt += Wfix;
+	double m[9], mn[9];
+	for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
+	for(int i = 0; i < 3; i++)
+		for(int j = 0; j < 3; j++) mn[3 * i + j] = dot3_rn(m[3 * i], m[3 * i + 1], m[3 * i + 2], pr->R[j], pr->R[3 + j], pr->R[6 + j]);
+	int b_old = 0, b_new = 0, n_seen = 0;
+	bool ovl = false;
+	for(int ddx = -1; ddx <= 1; ddx++) {
+		int ccx = ix + ddx;
+		if(sc.slab) {
+			if(ccx < 0 || ccx >= sc.nxl) continue; // beyond the halo
+		}
+		else {
+			if(sc.nxl == 2 && ddx < 0) continue; // two cells along x: -1 and +1 are the same neighbour
+			ccx = wrap_cell(ccx, sc.nxl);
+		}
+		for(int ddy = -1; ddy <= 1; ddy++) {
+			if(ny == 2 && ddy < 0) continue;
+			for(int ddz = -1; ddz <= 1; ddz++) {
+				if(nz == 2 && ddz < 0) continue;
+				const int c = (ccx * ny + wrap_cell(iy + ddy, ny)) * nz + wrap_cell(iz + ddz, nz);
+				for(int s = cell_start[c]; s < cell_start[c + 1]; s++) {
+					if(s == sp) continue;
+					n_seen++;
+					const double4 q4 = pos[s];
+					Vec3 d;
+					double d2 = min_image(sc, p_old, q4, d);
+					if(d2 >= 1. && d2 < sc.sqr_rcut) b_old += patches_bond_m(sc, d, d2, m, ori + 9ll * s) ? 1 : 0;
+					d2 = min_image(sc, p_new, q4, d);
+					if(d2 < 1.) ovl = true;
+					else if(d2 < sc.sqr_rcut) b_new += patches_bond_m(sc, d, d2, mn, ori + 9ll * s) ? 1 : 0;
+				}
+			}
+		}
+	}
+	tl.checks += 2ull * (unsigned long long) n_seen;
+	if(ovl) {
+		tl.ovl++;
+		return;
+	}
+	const int dE = b_old - b_new;
+	if(dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
+		double *p = reinterpret_cast<double *>(pos + sp);
+		p[0] = p_new.x;
+		p[1] = p_new.y;
+		p[2] = p_new.z;
+		posf[sp] = cell_relative(sc, p_new.x, p_new.y, p_new.z);
+		for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
+		tl.dbonds += b_new - b_old;
+		tl.acc++;
+		tl.wa += Wfix;
+	}
+}
+
+} // namespace pp
