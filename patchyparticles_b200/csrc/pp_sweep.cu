@@ -52,10 +52,14 @@ __global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ 
 	const uint4 y = philox4x32((uint32_t) cell, (uint32_t) t, sc.sweep_lo, sc.sweep_hi8 | 1u, sc.seed_lo, sc.seed_hi);
 	Proposal pr;
 	pr.pick = (int) __umulhi(x.x, (uint32_t) n_here);
-	pr.pad = 0;
 	pr.dx = __dmul_rn(__dsub_rn(u32_to_unit(x.y), 0.5), sc.disp_max);
 	pr.dy = __dmul_rn(__dsub_rn(u32_to_unit(x.z), 0.5), sc.disp_max);
 	pr.dz = __dmul_rn(__dsub_rn(u32_to_unit(x.w), 0.5), sc.disp_max);
+	{ // weight in the acceptance estimator: 1 / P(this displacement stays inside a uniformly shifted cell)
+		const double keep = __dmul_rn(__dmul_rn(__dsub_rn(1., __dmul_rn(fabs(pr.dx), sc.inv_w[0])), __dsub_rn(1., __dmul_rn(fabs(pr.dy), sc.inv_w[1]))),
+				__dsub_rn(1., __dmul_rn(fabs(pr.dz), sc.inv_w[2])));
+		pr.wfix = (unsigned int) (unsigned long long) __dmul_rn(__ddiv_rn(1., keep), 16777216.0);
+	}
 	const double theta = __dmul_rn(u32_to_unit(y.x), sc.theta_max);
 	pr.u_acc = __dmul_rn((double) ((((unsigned long long) y.y) << 21) | (((unsigned long long) y.z) >> 11)), 1.0 / 9007199254740992.0);
 	double ran1, ran2, ransq;
@@ -111,17 +115,10 @@ struct TileSmem {
 	Neighbourhood nb;
 	double x[kStageCap], y[kStageCap], z[kStageCap];
 	int slot[kStageCap];
-	double prop[14]; // R[9], dx, dy, dz, u_acc, (pick, pad)
+	double prop[14]; // R[9], dx, dy, dz, u_acc, (pick, wfix)
 	double m_old[9], m_new[9], pp_old[12], pp_new[12];
 	unsigned short cand[2 * kStageCap]; // staged index | (new ? 0x8000 : 0)
 };
-
-// weight of a non-confined trial in the acceptance estimator: 1 / P(this displacement stays in a cell)
-__device__ __forceinline__ unsigned long long trial_weight(const SimConst &sc, double dx, double dy, double dz) {
-	const double keep = __dmul_rn(__dmul_rn(__dsub_rn(1., __dmul_rn(fabs(dx), sc.inv_w[0])), __dsub_rn(1., __dmul_rn(fabs(dy), sc.inv_w[1]))),
-			__dsub_rn(1., __dmul_rn(fabs(dz), sc.inv_w[2])));
-	return (unsigned long long) __dmul_rn(__ddiv_rn(1., keep), 16777216.0);
-}
 
 template<int G>
 __host__ __device__ constexpr int sweep_threads() {
@@ -180,6 +177,7 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 			const double *R = ts.prop;
 			const double dx = ts.prop[9], dy = ts.prop[10], dz = ts.prop[11], u_acc = ts.prop[12];
 			const int pick = reinterpret_cast<const int *>(ts.prop + 13)[0];
+			const unsigned long long Wfix = (unsigned long long) reinterpret_cast<const unsigned int *>(ts.prop + 13)[1];
 			a_tries++;
 			const int sp = first + pick;
 			const int j_self = home_base + pick;
@@ -195,7 +193,6 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 				a_conf++;
 				continue;
 			}
-			const unsigned long long Wfix = trial_weight(sc, dx, dy, dz);
 			a_wt += Wfix;
 
 			// ---- distance tests of the old and new position (MC.c:233-241) --------------------
@@ -349,7 +346,7 @@ static int launch_pass_g(const SimConst &sc, int colour, const CellBuffers &cb, 
 	if(n_active > sc.N) n_active = sc.N;
 	const int tiles_per_block = kThreads / G;
 	long long blocks = (n_active + tiles_per_block - 1) / tiles_per_block;
-	const long long cap = 148ll * 32 * 16;
+	const long long cap = 148ll * 8 * 3; // three waves of resident blocks; tiles stride over the occupancy-sorted list
 	if(blocks > cap) blocks = cap;
 	if(blocks < 1) blocks = 1;
 	k_sweep_pass<G><<<(unsigned) blocks, kThreads, 0, st>>>(sc, colour, cb.cell_start, cb.work, cb.bins + kWorkStart, proposals, pos, ori, cb.posf, counters);

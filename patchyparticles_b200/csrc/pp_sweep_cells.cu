@@ -21,7 +21,7 @@
 //
 // The work list hands consecutive threads cells of equal occupancy, which keeps the lanes of a warp
 // in the same trial.
-#include "pp_kernels.cuh"
+#include "pp_trial_serial.cuh"
 
 #include <cuda_pipeline.h>
 
@@ -39,80 +39,6 @@ struct CellBlockCounters {
 	unsigned long long w_tries, w_accepted, pair_checks;
 };
 
-struct CellTally {
-	unsigned int tries, acc, conf, ovl;
-	int dbonds;
-	unsigned long long wt, wa, checks;
-};
-
-__device__ __forceinline__ unsigned long long trial_weight_cells(const SimConst &sc, double dx, double dy, double dz) {
-	const double keep = __dmul_rn(__dmul_rn(__dsub_rn(1., __dmul_rn(fabs(dx), sc.inv_w[0])), __dsub_rn(1., __dmul_rn(fabs(dy), sc.inv_w[1]))),
-			__dsub_rn(1., __dmul_rn(fabs(dz), sc.inv_w[2])));
-	return (unsigned long long) __dmul_rn(__ddiv_rn(1., keep), 16777216.0);
-}
-
-__device__ __forceinline__ int wrap_cell(int c, int n) {
-	c += (c < 0) ? n : 0;
-	c -= (c >= n) ? n : 0;
-	return c;
-}
-
-// Fallback for neighbourhoods that do not fit the staging area (dense crystals, tiny boxes are
-// handled by the tile kernel): the whole trial in FP64 straight from global memory.
-static __device__ __noinline__ void trial_unstaged(const SimConst &sc, const int *__restrict__ cell_start, double4 *pos, double *ori, float4 *posf,
-		const Proposal *pr, int cell, int ix, int iy, int iz, int sp, CellTally &tl) {
-	const int nx = sc.n_side[0], ny = sc.n_side[1], nz = sc.n_side[2];
-	const double4 p4 = pos[sp];
-	const Vec3 p_old = {p4.x, p4.y, p4.z};
-	const Vec3 p_new = {__dadd_rn(p4.x, pr->dx), __dadd_rn(p4.y, pr->dy), __dadd_rn(p4.z, pr->dz)};
-	int cx, cy, cz;
-	if(cell_index(sc, p_new.x, p_new.y, p_new.z, cx, cy, cz) != cell) {
-		tl.conf++;
-		return;
-	}
-	const unsigned long long Wfix = trial_weight_cells(sc, pr->dx, pr->dy, pr->dz);
-	tl.wt += Wfix;
-	double m[9], mn[9];
-	for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
-	for(int i = 0; i < 3; i++)
-		for(int j = 0; j < 3; j++) mn[3 * i + j] = dot3_rn(m[3 * i], m[3 * i + 1], m[3 * i + 2], pr->R[j], pr->R[3 + j], pr->R[6 + j]);
-	int b_old = 0, b_new = 0, n_seen = 0;
-	bool ovl = false;
-	for(int ddx = -1; ddx <= 1; ddx++)
-		for(int ddy = -1; ddy <= 1; ddy++)
-			for(int ddz = -1; ddz <= 1; ddz++) {
-				const int c = (wrap_cell(ix + ddx, nx) * ny + wrap_cell(iy + ddy, ny)) * nz + wrap_cell(iz + ddz, nz);
-				for(int s = cell_start[c]; s < cell_start[c + 1]; s++) {
-					if(s == sp) continue;
-					n_seen++;
-					const double4 q4 = pos[s];
-					Vec3 d;
-					double d2 = min_image(sc, p_old, q4, d);
-					if(d2 >= 1. && d2 < sc.sqr_rcut) b_old += patches_bond_m(sc, d, d2, m, ori + 9ll * s) ? 1 : 0;
-					d2 = min_image(sc, p_new, q4, d);
-					if(d2 < 1.) ovl = true;
-					else if(d2 < sc.sqr_rcut) b_new += patches_bond_m(sc, d, d2, mn, ori + 9ll * s) ? 1 : 0;
-				}
-			}
-	tl.checks += 2ull * (unsigned long long) n_seen;
-	if(ovl) {
-		tl.ovl++;
-		return;
-	}
-	const int dE = b_old - b_new;
-	if(dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
-		double *p = reinterpret_cast<double *>(pos + sp);
-		p[0] = p_new.x;
-		p[1] = p_new.y;
-		p[2] = p_new.z;
-		posf[sp] = cell_relative(sc, p_new.x, p_new.y, p_new.z);
-		for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
-		tl.dbonds += b_new - b_old;
-		tl.acc++;
-		tl.wa += Wfix;
-	}
-}
-
 __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_constant__ SimConst sc, int colour, const int *__restrict__ cell_start,
 		const int *__restrict__ work, const int *__restrict__ work_start, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
 		float4 *posf, Counters *__restrict__ counters) {
@@ -128,7 +54,7 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 	const int nx = sc.n_side[0], ny = sc.n_side[1], nz = sc.n_side[2];
 	const float wx = (float) sc.cell_w[0], wy = (float) sc.cell_w[1], wz = (float) sc.cell_w[2];
 	const float thr = (float) sc.sqr_rcut + kScreenBand;
-	CellTally tl = {0, 0, 0, 0, 0, 0, 0, 0};
+	Tally tl = {0, 0, 0, 0, 0, 0, 0, 0};
 
 	for(int wi = w_begin + blockIdx.x * kCellThreads + tid; wi < w_end; wi += gridDim.x * kCellThreads) {
 		const int cell = work[wi];
@@ -183,7 +109,7 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 			const int sp = first + pick;
 			tl.tries++;
 			if(!staged) {
-				trial_unstaged(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
+				trial_serial(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
 				continue;
 			}
 			const double dx = pr->dx, dy = pr->dy, dz = pr->dz;
@@ -195,7 +121,7 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 				tl.conf++;
 				continue;
 			}
-			const unsigned long long Wfix = trial_weight_cells(sc, dx, dy, dz);
+			const unsigned long long Wfix = (unsigned long long) pr->wfix;
 			tl.wt += Wfix;
 			const int j_self = self_base + pick;
 			const float4 f_old = s_stage[j_self][tid];
@@ -231,7 +157,7 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 			}
 			tl.checks += 2ull * (unsigned long long) (total - 1);
 			if(n_cand > kCandCap) { // cannot happen for hard spheres with r_cut < 1.5; kept for safety
-				trial_unstaged(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
+				trial_serial(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
 				tl.wt -= Wfix;
 				tl.checks -= 2ull * (unsigned long long) (total - 1);
 				continue;
