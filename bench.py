@@ -264,6 +264,9 @@ class Arm:
     def check_energy(self):
         return self.drv.check_energy()
 
+    def download(self):
+        return self.drv.download()
+
     def cells(self):
         return list(self.eng.observables().n_side)
 
@@ -279,6 +282,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--relax-sweeps", type=int, default=300,
+                    help="untimed sweeps that turn the lattice-thinned synthetic configuration into a fluid before anything is measured")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # N = 1: BASELINE.json configs[1] (N = 65536).  N > 1: configs[3], one N = 4M system sharded into x slabs (strong scaling)
@@ -315,7 +320,7 @@ def main():
 
     N, rho, T = WORKLOADS[w]
     K, W = args.steps, max(args.warmup, 3)
-    box, r, m, data_desc, _ = make_configuration(w)
+    box, r, m, data_desc, rrr_path = make_configuration(w)
     stream = torch.cuda.current_stream()
     arm = Arm(pkg, args, w, rank, local_rank, world, sharded)
     eng = arm.eng
@@ -326,6 +331,12 @@ def main():
     attempts_per_step = float(N) * n_systems      # whole-job attempts per step
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # ---- untimed relaxation of the lattice-thinned synthetic configuration into a fluid ------------------
+    if rrr_path is None and args.relax_sweeps > 0:
+        arm.sweep(args.relax_sweeps, sync=True)
+        r, m = arm.download()
+        data_desc += f", relaxed by {args.relax_sweeps} untimed sweeps"
 
     # ---- warm-up ----------------------------------------------------------------------------
     arm.sweep(W, sync=True)

@@ -58,8 +58,10 @@ typedef struct pp_params {
 	int Lx_reference_sign;      /* 1: reproduce exp(+dE/T) of MC.c:562; 0: Metropolis exp(-dE/T) */
 	uint64_t seed;              /* Seed                                             system.c:71-75 */
 	int device;                 /* CUDA device ordinal */
-	int lanes_per_cell;         /* sweep-kernel tile width: 0 = default; 4, 8, 16 or 32 */
+	int lanes_per_cell;         /* 0 = default (hybrid: sparse cells one thread each, crowded cells one tile each);
+	                               1 = every cell one thread; 4, 8, 16, 32 = every cell one tile of that width */
 	int use_graph;              /* 1: replay the per-sweep launch sequence as a CUDA graph */
+	int cells_max_occupancy;    /* hybrid mode: cells with at most this many particles go to the thread-per-cell kernel; -1 = default (3) */
 	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
 } pp_params;
 

@@ -100,6 +100,11 @@ struct pp_handle {
 	bool slab_pending;   // a classify has been done and waits for pp_slab_sweep_rebuild
 	int layer_slots[6];  // slot offsets: left halo begin, first owned begin, first owned end, last owned begin, right halo begin, right halo end
 
+	// the two sweep kernels of a colour pass run concurrently: crowded cells (tile kernel) on `stream`, sparsely
+	// populated ones (thread-per-cell kernel) on `stream2`
+	cudaStream_t stream2;
+	cudaEvent_t ev_a, ev_b;
+
 	// profiling
 	bool profiling;
 	long long launches[PP_K_CLASSES];
@@ -285,6 +290,51 @@ void prof_end(pp_handle *h, int kclass, int n_launches) {
 	}
 }
 
+// Which sweep kernel gets which cells.  lanes_per_cell = 1: every cell to the thread-per-cell kernel; 4..32: every
+// cell to the tile kernel of that width; 0 (default): cells with at most cells_max_occupancy members to the
+// thread-per-cell kernel, the crowded ones to the tile kernel, concurrently.  The thread-per-cell kernel needs
+// three distinct cells per axis.
+int cells_occupancy_limit(const pp_handle *h) {
+	const bool grid_ok = (h->slab_world > 1 || h->n_side[0] >= 4) && h->n_side[1] >= 4 && h->n_side[2] >= 4;
+	if(!grid_ok) return 0;
+	if(h->prm.lanes_per_cell == 1) return kWorkBuckets - 1;
+	if(h->prm.lanes_per_cell != 0) return 0;
+	if(h->prm.cells_max_occupancy >= 0) return h->prm.cells_max_occupancy < kWorkBuckets ? h->prm.cells_max_occupancy : kWorkBuckets - 1;
+	return (h->N >= 400000) ? 3 : 0; // small systems are bound by the serial chain of a cell: tiles only (profiles/README.md)
+}
+
+int tile_lanes(const pp_handle *h) {
+	const int l = h->prm.lanes_per_cell;
+	if(l == 4 || l == 8 || l == 16 || l == 32) return l;
+	return (h->N >= 400000) ? 8 : 16; // measured on B200: profiles/README.md
+}
+
+// the colour passes `first_pass .. first_pass + n_pass - 1` of one sweep (pass order: x parity slowest)
+int launch_passes(pp_handle *h, const SimConst &sc, int first_pass, int n_pass) {
+	const int limit = cells_occupancy_limit(h), lanes = tile_lanes(h);
+	long long n_active = (long long) (sc.nxl / 2 + 1) * (sc.n_side[1] / 2) * (sc.n_side[2] / 2);
+	if(n_active > sc.N) n_active = sc.N;
+	int nl = 0;
+	if(limit > 0) { // the second stream joins after everything already queued on the first
+		cudaEventRecord(h->ev_a, h->stream);
+		cudaStreamWaitEvent(h->stream2, h->ev_a, 0);
+	}
+	for(int pass = first_pass; pass < first_pass + n_pass; pass++) {
+		const int colour = ((pass >> 2) & 1) | (((pass >> 1) & 1) << 1) | ((pass & 1) << 2);
+		const int *ranges = h->cb.bins + kWorkRanges + 4 * colour;
+		nl += launch_sweep_pass(sc, ranges, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
+		if(limit > 0) {
+			nl += launch_sweep_cells(sc, ranges + 2, n_active, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream2);
+			// the next pass (either kernel) starts when both kernels of this one are done
+			cudaEventRecord(h->ev_a, h->stream);
+			cudaEventRecord(h->ev_b, h->stream2);
+			cudaStreamWaitEvent(h->stream, h->ev_b, 0);
+			cudaStreamWaitEvent(h->stream2, h->ev_a, 0);
+		}
+	}
+	return nl;
+}
+
 // slab decomposition: after a sort, particles outside the held layers sit in the trash cell at the end of the
 // arrays and are dropped; the slot ranges of the boundary and halo layers are cached for the halo refresh
 int slab_after_sort(pp_handle *h) {
@@ -310,7 +360,7 @@ int rebin(pp_handle *h, const double *shift) {
 	const SimConst sc = make_const(h, h->box, h->shift);
 	const int np = (h->cp + 1) % 3, no = h->co ^ 1;
 	prof_begin(h);
-	const int nl = launch_cell_build(sc, h->cb, view(h, h->cp, h->co), view(h, np, no), h->slot_of, h->stream);
+	const int nl = launch_cell_build(sc, h->cb, view(h, h->cp, h->co), view(h, np, no), h->slot_of, cells_occupancy_limit(h), h->stream);
 	prof_end(h, PP_K_CELLS, nl);
 	h->cp = np;
 	h->co = no;
@@ -532,6 +582,7 @@ void pp_default_params(pp_params *p) {
 	p->Lx_reference_sign = 1;
 	p->seed = 12345;
 	p->lanes_per_cell = 0;
+	p->cells_max_occupancy = -1;
 }
 
 const char *pp_last_error(const pp_handle *h) {
@@ -567,6 +618,9 @@ int pp_create(const pp_params *params, pp_handle **out) {
 	CUDA_OK(h, cudaMemset(h->cb.bins, 0, sizeof(int) * kBinInts));
 	CUDA_OK(h, cudaEventCreate(&h->ev0));
 	CUDA_OK(h, cudaEventCreate(&h->ev1));
+	CUDA_OK(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+	CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+	CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
 	h->r_cut = 1. + params->kf_delta; // system.c:249
 	base_patches_host(h->base);
 	if(h->prm.lanes_per_cell != 1 && h->prm.lanes_per_cell != 4 && h->prm.lanes_per_cell != 8 && h->prm.lanes_per_cell != 16 && h->prm.lanes_per_cell != 32)
@@ -590,6 +644,9 @@ int pp_destroy(pp_handle *h) {
 	cudaFreeHost(h->h_counters);
 	if(h->ev0) cudaEventDestroy(h->ev0);
 	if(h->ev1) cudaEventDestroy(h->ev1);
+	if(h->ev_a) cudaEventDestroy(h->ev_a);
+	if(h->ev_b) cudaEventDestroy(h->ev_b);
+	if(h->stream2) cudaStreamDestroy(h->stream2);
 	if(h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 	free(h);
 	return 0;
@@ -759,17 +816,7 @@ int pp_sweep(pp_handle *h, long long nsteps) {
 		const int nr = launch_proposals_for_sweep(sc, h->cb, h->d_proposals, h->stream);
 		prof_end(h, PP_K_RNG, nr);
 		prof_begin(h);
-		int nl = 0;
-		// lanes_per_cell: 1 = one thread per cell (throughput, large N), 4..32 = one tile per cell (latency, small N)
-		int lanes = h->prm.lanes_per_cell;
-		if(lanes == 0) lanes = (h->N >= 400000) ? 8 : 16; // measured on B200: profiles/README.md
-		if(lanes == 1 && (h->n_side[0] < 4 || h->n_side[1] < 4 || h->n_side[2] < 4)) lanes = 8;
-		for(int pass = 0; pass < 8; pass++) {
-			// pass order: x parity slowest (a slab decomposition along x then exchanges halos twice per sweep)
-			const int colour = ((pass >> 2) & 1) | (((pass >> 1) & 1) << 1) | ((pass & 1) << 2);
-			if(lanes == 1) nl += launch_sweep_cells(sc, colour, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
-			else nl += launch_sweep_pass(sc, colour, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
-		}
+		const int nl = launch_passes(h, sc, 0, 8);
 		prof_end(h, PP_K_SWEEP, nl);
 		h->step++;
 	}
@@ -1019,7 +1066,7 @@ int pp_slab_sweep_rebuild(pp_handle *h) {
 	memcpy(h->shift, h->pending_shift, sizeof(h->shift));
 	const SimConst sc = make_const(h, h->box, h->shift);
 	prof_begin(h);
-	const int nl = launch_cell_build(sc, h->cb, view(h, tp, to), view(h, h->cp, h->co), h->slot_of, h->stream);
+	const int nl = launch_cell_build(sc, h->cb, view(h, tp, to), view(h, h->cp, h->co), h->slot_of, cells_occupancy_limit(h), h->stream);
 	prof_end(h, PP_K_CELLS, nl);
 	CUDA_OK(h, cudaGetLastError());
 	h->cells_valid = true;
@@ -1040,14 +1087,8 @@ int pp_slab_pass_block(pp_handle *h, int cx) {
 		const int nr = launch_proposals_for_sweep(sc, h->cb, h->d_proposals, h->stream);
 		prof_end(h, PP_K_RNG, nr);
 	}
-	int lanes = h->prm.lanes_per_cell;
-	if(lanes == 0 || lanes == 1) lanes = (h->N >= 400000) ? 8 : 16;
 	prof_begin(h);
-	int nl = 0;
-	for(int sub = 0; sub < 4; sub++) {
-		const int colour = cx | (((sub >> 1) & 1) << 1) | ((sub & 1) << 2); // same order as pp_sweep: passes 4 cx .. 4 cx + 3
-		nl += launch_sweep_pass(sc, colour, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
-	}
+	const int nl = launch_passes(h, sc, 4 * cx, 4);
 	prof_end(h, PP_K_SWEEP, nl);
 	CUDA_OK(h, cudaGetLastError());
 	return 0;

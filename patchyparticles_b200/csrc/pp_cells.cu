@@ -106,24 +106,49 @@ __global__ void __launch_bounds__(256) k_cell_scatter(int N, const int *__restri
 	perm[cell_start[c] + atomicAdd(cell_fill + c, 1)] = i;
 }
 
-// bin of a non-empty cell in the work lists: colour-major, occupancy descending inside a colour
-__device__ __forceinline__ int work_bin(const SimConst &sc, int c, int n) {
-	const int nyz = sc.n_side[1] * sc.n_side[2];
-	const int ix = c / nyz, iy = (c - ix * nyz) / sc.n_side[2], iz = c - ix * nyz - iy * sc.n_side[2];
-	const int colour = ((ix + sc.x_lo) & 1) | ((iy & 1) << 1) | ((iz & 1) << 2); // parity of the GLOBAL layer
-	const int bucket = n < kWorkBuckets ? n : kWorkBuckets;        // 1 .. kWorkBuckets
-	return colour * kWorkBuckets + (kWorkBuckets - bucket);           // big cells first
+// particles in the 27-cell neighbourhood of an owned cell (periodic wrap, or the slab's halo layers along x)
+__device__ __forceinline__ int neighbourhood_total(const SimConst &sc, const int *__restrict__ cell_start, int ix, int iy, int iz) {
+	const int ny = sc.n_side[1], nz = sc.n_side[2];
+	int total = 0;
+	for(int dx = -1; dx <= 1; dx++) {
+		int cx = ix + dx;
+		if(!sc.slab) {
+			cx += (cx < 0) ? sc.nxl : 0;
+			cx -= (cx >= sc.nxl) ? sc.nxl : 0;
+		}
+		for(int dy = -1; dy <= 1; dy++) {
+			int cy = iy + dy;
+			cy += (cy < 0) ? ny : 0;
+			cy -= (cy >= ny) ? ny : 0;
+			const int col = (cx * ny + cy) * nz;
+			const int z0 = iz > 0 ? iz - 1 : 0, z1 = iz < nz - 1 ? iz + 1 : nz - 1;
+			total += cell_start[col + z1 + 1] - cell_start[col + z0]; // the z-run is contiguous
+			if(iz == 0) total += cell_start[col + nz] - cell_start[col + nz - 1];
+			else if(iz == nz - 1) total += cell_start[col + 1] - cell_start[col];
+		}
+	}
+	return total;
 }
 
-// per cell: order its particles by id (insertion sort; a handful of particles) and count its work bin
+// bin of a non-empty cell in the work lists: colour-major, occupancy descending inside a colour.  A cell whose
+// neighbourhood does not fit the staging area of the thread-per-cell kernel is filed with the most crowded ones,
+// which always go to the tile kernel.
+__device__ __forceinline__ int work_bin(const SimConst &sc, int ix, int iy, int iz, int n, bool dense) {
+	const int colour = ((ix + sc.x_lo) & 1) | ((iy & 1) << 1) | ((iz & 1) << 2); // parity of the GLOBAL layer
+	const int bucket = (dense || n >= kWorkBuckets) ? kWorkBuckets : n;            // 1 .. kWorkBuckets
+	return colour * kWorkBuckets + (kWorkBuckets - bucket);                         // big cells first
+}
+
+// per cell: order its particles by id (insertion sort; a handful of particles), choose and count its work bin
 __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start, int *__restrict__ perm,
-		const int *__restrict__ pid_src, int *__restrict__ bin_count) {
+		const int *__restrict__ pid_src, int *__restrict__ bin_count, int *__restrict__ cell_bin, int cells_max_occupancy, int cells_nb_cap) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if(c >= sc.n_cells) return;
 	const int b = cell_start[c], e = cell_start[c + 1];
 	if(e == b) return;
-	const int layer = c / (sc.n_side[1] * sc.n_side[2]);
-	const bool owned = layer >= sc.own_lo && layer < sc.own_hi;
+	const int nyz = sc.n_side[1] * sc.n_side[2];
+	const int ix = c / nyz, iy = (c - ix * nyz) / sc.n_side[2], iz = c - ix * nyz - iy * sc.n_side[2];
+	const bool owned = ix >= sc.own_lo && ix < sc.own_hi;
 	for(int a = b + 1; a < e; a++) {
 		const int src = perm[a];
 		const int key = pid_src[src];
@@ -134,11 +159,15 @@ __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimC
 		}
 		perm[k + 1] = src;
 	}
-	if(owned) atomicAdd(bin_count + work_bin(sc, c, e - b), 1); // halo cells are never moved here
+	if(!owned) return; // halo cells are never moved here
+	const bool dense = (e - b <= cells_max_occupancy) && neighbourhood_total(sc, cell_start, ix, iy, iz) > cells_nb_cap;
+	const int bin = work_bin(sc, ix, iy, iz, e - b, dense);
+	cell_bin[c] = bin;
+	atomicAdd(bin_count + bin, 1);
 }
 
 // one warp: exclusive scan of the 8 * kWorkBuckets bins; work_start[colour] marks the colour boundaries
-__global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__ bin_start, int *__restrict__ work_start) {
+__global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__ bin_start, int *__restrict__ ranges, int cells_max_occupancy) {
 	__shared__ int s[8 * kWorkBuckets + 1];
 	if(threadIdx.x == 0) {
 		int run = 0;
@@ -150,17 +179,24 @@ __global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__
 	}
 	__syncthreads();
 	for(int b = threadIdx.x; b <= 8 * kWorkBuckets; b += blockDim.x) bin_start[b] = s[b];
-	if(threadIdx.x <= 8) work_start[threadIdx.x] = s[threadIdx.x * kWorkBuckets];
+	if(threadIdx.x < 8) { // split each colour's list: crowded cells (tile kernel) first, then cells with <= cells_max_occupancy members
+		const int c = threadIdx.x, m = cells_max_occupancy < kWorkBuckets ? cells_max_occupancy : kWorkBuckets;
+		const int split = s[c * kWorkBuckets + (kWorkBuckets - m)];
+		ranges[4 * c + 0] = s[c * kWorkBuckets];
+		ranges[4 * c + 1] = split;
+		ranges[4 * c + 2] = split;
+		ranges[4 * c + 3] = s[(c + 1) * kWorkBuckets];
+	}
 }
 
 __global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
-		const int *__restrict__ bin_start, int *__restrict__ bin_fill, int *__restrict__ work) {
+		const int *__restrict__ bin_start, int *__restrict__ bin_fill, const int *__restrict__ cell_bin, int *__restrict__ work) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if(c >= sc.n_cells) return;
 	const int n = cell_start[c + 1] - cell_start[c];
 	const int layer = c / (sc.n_side[1] * sc.n_side[2]);
 	if(n == 0 || layer < sc.own_lo || layer >= sc.own_hi) return;
-	const int bin = work_bin(sc, c, n);
+	const int bin = cell_bin[c];
 	work[bin_start[bin] + atomicAdd(bin_fill + bin, 1)] = c;
 }
 
@@ -188,7 +224,8 @@ __global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int
 }
 
 // ---------------------------------------------------------------------------------------------
-int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, cudaStream_t st) {
+int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, int cells_max_occupancy,
+		cudaStream_t st) {
 	const int N = sc.N;
 	const int nc = sc.n_cells + 1; // + the trash cell that collects particles outside the held layers
 	cudaMemsetAsync(cb.bins, 0, sizeof(int) * kBinInts, st);
@@ -205,9 +242,9 @@ int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView
 	k_scan_sums<<<1, 1024, 0, st>>>(cb.tile_sums, n_tiles, cb.cell_start + nc);
 	k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_start, cb.tile_sums, nc);
 	k_cell_scatter<<<nb, 256, 0, st>>>(N, cb.cell_of, cb.cell_start, cb.cell_fill, cb.perm);
-	k_cell_order<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.perm, src.pid, cb.bins + kBinCount);
-	k_bins_scan<<<1, 160, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkStart);
-	k_work_scatter<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.bins + kBinStart, cb.bins + kBinFill, cb.work);
+	k_cell_order<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.perm, src.pid, cb.bins + kBinCount, cb.cell_fill, cells_max_occupancy, kCellsNbCap);
+	k_bins_scan<<<1, 160, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkRanges, cells_max_occupancy);
+	k_work_scatter<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.bins + kBinStart, cb.bins + kBinFill, cb.cell_fill, cb.work);
 	k_cell_gather_pos<<<nb, 256, 0, st>>>(sc, cb.perm, cb.cell_of, src.pos, src.pid, dst.pos, dst.pid, slot_of, cb.cell_sorted, cb.posf);
 	const long long n9 = 9ll * N;
 	k_cell_gather_ori<<<(unsigned) ((n9 + 255) / 256), 256, 0, st>>>(n9, cb.perm, src.ori, dst.ori);

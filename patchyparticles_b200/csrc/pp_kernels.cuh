@@ -14,11 +14,12 @@ struct StateView {
 
 // work lists of the sweep: 8 colours x kWorkBuckets occupancy buckets (descending occupancy)
 constexpr int kWorkBuckets = 16;
+constexpr int kCellsNbCap = 32; // neighbours the thread-per-cell sweep kernel can stage; cells with more go to the tile kernel
 constexpr int kBinCount = 0;                              // [8 * kWorkBuckets] cells per bin
 constexpr int kBinStart = 8 * kWorkBuckets;               // [8 * kWorkBuckets + 1] exclusive prefix
 constexpr int kBinFill = kBinStart + 8 * kWorkBuckets + 1; // [8 * kWorkBuckets] scatter cursors
-constexpr int kWorkStart = kBinFill + 8 * kWorkBuckets;   // [9] first work item of each colour
-constexpr int kBinInts = kWorkStart + 16;
+constexpr int kWorkRanges = kBinFill + 8 * kWorkBuckets;  // [8][4] per colour: tile-kernel range {begin, end}, thread-kernel range {begin, end}
+constexpr int kBinInts = kWorkRanges + 32;
 
 struct CellBuffers {
 	int *cell_of;     // N: cell of each particle in source order
@@ -52,18 +53,20 @@ struct ProposalIO {
 	int *dE, *overlap, *accept, *cell_changed;
 };
 
-// K1: returns the number of kernels launched
-int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, cudaStream_t st);
+// K1: returns the number of kernels launched.  cells_max_occupancy: cells with at most that many members go to
+// the thread-per-cell sweep kernel, the more crowded ones to the tile kernel (0: everything to the tile kernel)
+int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, int cells_max_occupancy,
+		cudaStream_t st);
 
 // K2a: proposals of all N trials of one sweep (trial t of a cell lives at index cell_start[cell] + t)
 int launch_proposals_for_sweep(const SimConst &sc, const CellBuffers &cb, Proposal *proposals, cudaStream_t st);
-// K2b: one colour pass of the checkerboard sweep
-int launch_sweep_pass(const SimConst &sc, int colour, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
+// K2b: one colour pass of the checkerboard sweep over the work items [range[0], range[1]) (device-resident range):
+// tile of `lanes` threads per cell ...
+int launch_sweep_pass(const SimConst &sc, const int *range, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
 		Counters *counters, cudaStream_t st);
-
-// K2b, throughput variant: one thread per cell (needs at least 4 cells per axis)
-int launch_sweep_cells(const SimConst &sc, int colour, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori, Counters *counters,
-		cudaStream_t st);
+// ... or one thread per cell (sparsely populated cells; needs at least 3 distinct cells per axis)
+int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
+		double *ori, Counters *counters, cudaStream_t st);
 
 // K3: full bond count + overlap flag into counters->bonds / counters->overlap (zeroed by the launcher)
 int launch_total_bonds(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, Counters *counters, cudaStream_t st);

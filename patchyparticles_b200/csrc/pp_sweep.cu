@@ -126,8 +126,8 @@ __host__ __device__ constexpr int sweep_threads() {
 }
 
 template<int G>
-__global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) k_sweep_pass(const __grid_constant__ SimConst sc, int colour,
-		const int *__restrict__ cell_start, const int *__restrict__ work, const int *__restrict__ work_start, const Proposal *__restrict__ proposals,
+__global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) k_sweep_pass(const __grid_constant__ SimConst sc, const int *__restrict__ range,
+		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals,
 		double4 *pos, double *ori, float4 *posf, Counters *__restrict__ counters) {
 	constexpr int kThreads = sweep_threads<G>();
 	constexpr int kTiles = kThreads / G;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 	if(threadIdx.x == 0) s_cnt = BlockCounters{0, 0, 0, 0, 0, 0, 0, 0};
 	__syncthreads();
 
-	const int w_begin = work_start[colour], w_end = work_start[colour + 1];
+	const int w_begin = range[0], w_end = range[1];
 	const int nyz = sc.n_side[1] * sc.n_side[2];
 	// per-tile tallies (kept by every lane, flushed by lane 0)
 	unsigned int a_tries = 0, a_acc = 0, a_conf = 0, a_ovl = 0;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 }
 
 template<int G>
-static int launch_pass_g(const SimConst &sc, int colour, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori, Counters *counters,
+static int launch_pass_g(const SimConst &sc, const int *range, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori, Counters *counters,
 		cudaStream_t st) {
 	constexpr int kThreads = sweep_threads<G>();
 	// the number of non-empty cells of this colour lives on the device (work_start); size the grid for
@@ -349,21 +349,21 @@ static int launch_pass_g(const SimConst &sc, int colour, const CellBuffers &cb, 
 	const long long cap = 148ll * 8 * 3; // three waves of resident blocks; tiles stride over the occupancy-sorted list
 	if(blocks > cap) blocks = cap;
 	if(blocks < 1) blocks = 1;
-	k_sweep_pass<G><<<(unsigned) blocks, kThreads, 0, st>>>(sc, colour, cb.cell_start, cb.work, cb.bins + kWorkStart, proposals, pos, ori, cb.posf, counters);
+	k_sweep_pass<G><<<(unsigned) blocks, kThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters);
 	return 1;
 }
 
-int launch_sweep_pass(const SimConst &sc, int colour, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
+int launch_sweep_pass(const SimConst &sc, const int *range, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
 		Counters *counters, cudaStream_t st) {
 	switch(lanes) {
 	case 4:
-		return launch_pass_g<4>(sc, colour, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<4>(sc, range, cb, proposals, pos, ori, counters, st);
 	case 8:
-		return launch_pass_g<8>(sc, colour, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<8>(sc, range, cb, proposals, pos, ori, counters, st);
 	case 16:
-		return launch_pass_g<16>(sc, colour, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<16>(sc, range, cb, proposals, pos, ori, counters, st);
 	default:
-		return launch_pass_g<32>(sc, colour, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<32>(sc, range, cb, proposals, pos, ori, counters, st);
 	}
 }
 

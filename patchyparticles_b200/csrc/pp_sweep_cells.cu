@@ -3,24 +3,23 @@
 // Same algorithm, same random streams and bit-identical trajectories as the tile kernel in
 // pp_sweep.cu (both are checked against the serial restatement in oracle/pp_oracle.c); what changes
 // is the mapping onto the machine.  A thread walks its cell's trials on its own, so nothing is
-// computed redundantly, shuffled or reduced: ~9x fewer warp instructions per trial than the tile
-// kernel.  The price is a long dependent chain per thread, so the kernel is organised around
-// memory-level parallelism:
+// computed redundantly, shuffled or reduced: ~3-4x fewer warp instructions per trial than the tile
+// kernel.  The price is a serial chain per cell, so the engine routes only sparsely populated cells
+// here (at most kCellsMaxOccupancy members: >95 % of the cells of a fluid) and the crowded ones to
+// the tile kernel, both running concurrently on two streams.  The work list hands consecutive
+// threads cells of equal occupancy, which keeps the lanes of a warp in the same trial.
 //
 //   per cell   the FP32 shadow positions (float4: offset inside the cell + the cell's z index) of the
-//              whole 27-cell neighbourhood are brought into shared memory with cp.async -- nine
-//              contiguous z-runs, all copies in flight at once, one wait;
+//              27-cell neighbourhood are brought into shared memory with cp.async -- all copies in
+//              flight at once, one wait; each entry is tagged with its slot and its neighbour-cell code;
 //   per trial  1. FP32 pre-screen of the staged neighbours for the old and the new position; a pair
 //                 is a candidate when its FP32 squared distance is below r_cut^2 + 1e-3 (the FP32
 //                 error is < 1e-5, so no pair the FP64 test would put inside the shell, or flag as
 //                 overlapping, is ever dropped);
 //              2. FP64, reference operation order, on the candidates only (their double positions
-//                 are fetched four at a time): overlap of the new position (MC.c:240), shell test
+//                 are fetched two at a time): overlap of the new position (MC.c:240), shell test
 //                 (MC.c:241), orientation tests (MC.c:249-261);
 //              3. Metropolis rule (MC.c:332), write-back of position, orientation, FP32 shadow.
-//
-// The work list hands consecutive threads cells of equal occupancy, which keeps the lanes of a warp
-// in the same trial.
 #include "pp_trial_serial.cuh"
 
 #include <cuda_pipeline.h>
@@ -28,10 +27,12 @@
 namespace pp {
 
 constexpr int kCellThreads = 64;
-constexpr int kNbCap = 32;                   // staged neighbours per cell (mean 24 at rho = 0.6)
-constexpr int kCandCap = 24;                 // candidates per trial
+constexpr int kNbCap = kCellsNbCap;          // staged neighbours per cell; the cell build routes denser cells to the tile kernel
+constexpr int kCandCap = kCellsNbCap;        // candidates per trial (at most one entry per neighbour)
 constexpr float kScreenBand = 1e-3f;         // FP32 safety band around r_cut^2
 constexpr unsigned kNearOld = 0x40u, kNearNew = 0x80u, kIdxMask = 0x3fu;
+constexpr int kCodeShift = 26;               // staged tag: slot | neighbour-cell code << 26
+constexpr unsigned kSlotMask = (1u << kCodeShift) - 1u;
 
 struct CellBlockCounters {
 	unsigned int tries, accepted, confined, overlapped;
@@ -39,67 +40,57 @@ struct CellBlockCounters {
 	unsigned long long w_tries, w_accepted, pair_checks;
 };
 
-__global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_constant__ SimConst sc, int colour, const int *__restrict__ cell_start,
-		const int *__restrict__ work, const int *__restrict__ work_start, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
+__global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
+		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
 		float4 *posf, Counters *__restrict__ counters) {
 	__shared__ __align__(16) float4 s_stage[kNbCap][kCellThreads]; // [entry][thread]: conflict-free 16-byte accesses
-	__shared__ int s_slot[kNbCap][kCellThreads];
 	__shared__ unsigned char s_cand[kCandCap][kCellThreads];
+	__shared__ float s_off[27][3]; // offset of neighbour cell `code` from the home cell
 	__shared__ CellBlockCounters s_cnt;
 	const int tid = threadIdx.x;
 	if(tid == 0) s_cnt = CellBlockCounters{0, 0, 0, 0, 0, 0, 0, 0};
+	if(tid < 27) {
+		s_off[tid][0] = (float) (tid / 9 - 1) * (float) sc.cell_w[0];
+		s_off[tid][1] = (float) ((tid / 3) % 3 - 1) * (float) sc.cell_w[1];
+		s_off[tid][2] = (float) (tid % 3 - 1) * (float) sc.cell_w[2];
+	}
 	__syncthreads();
 
-	const int w_begin = work_start[colour], w_end = work_start[colour + 1];
-	const int nx = sc.n_side[0], ny = sc.n_side[1], nz = sc.n_side[2];
-	const float wx = (float) sc.cell_w[0], wy = (float) sc.cell_w[1], wz = (float) sc.cell_w[2];
+	const int w_begin = range[0], w_end = range[1];
+	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
 	const float thr = (float) sc.sqr_rcut + kScreenBand;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0, 0};
 
 	for(int wi = w_begin + blockIdx.x * kCellThreads + tid; wi < w_end; wi += gridDim.x * kCellThreads) {
 		const int cell = work[wi];
-		const int ix = cell / (ny * nz), iy = (cell - ix * ny * nz) / nz, iz = cell - ix * ny * nz - iy * nz;
+		const int ix = cell / nyz, iy = (cell - ix * nyz) / nz, iz = cell - ix * nyz - iy * nz;
 		const int first = cell_start[cell];
 		const int n_here = cell_start[cell + 1] - first;
 
-		// ---- stage the neighbourhood: 9 z-runs (+ the wrapped end cell), all copies in flight ------
+		// ---- stage the 27-cell neighbourhood: all copies in flight, one wait ------------------------------
 		int total = 0, self_base = 0;
-		int ccount[9]; // staged entries per (dx, dy) column
-		{
-			int rb[9], re[9], rb2[9], re2[9];
-			const int z0 = iz > 0 ? iz - 1 : 0, z1 = iz < nz - 1 ? iz + 1 : nz - 1;
+#pragma unroll 3
+		for(int c = 0; c < 9; c++) {
+			int cx = ix + c / 3 - 1;
+			if(!sc.slab) cx = wrap_cell(cx, sc.nxl); // (slab: an owned layer always has both x neighbours in the held range)
+			const int col = (cx * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
 #pragma unroll
-			for(int c = 0; c < 9; c++) {
-				const int col = (wrap_cell(ix + c / 3 - 1, nx) * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
-				rb[c] = cell_start[col + z0];
-				re[c] = cell_start[col + z1 + 1];
-				rb2[c] = re2[c] = 0;
-				if(iz == 0) {
-					rb2[c] = cell_start[col + nz - 1];
-					re2[c] = cell_start[col + nz];
-				}
-				else if(iz == nz - 1) {
-					rb2[c] = cell_start[col];
-					re2[c] = cell_start[col + 1];
-				}
-			}
-#pragma unroll
-			for(int c = 0; c < 9; c++) {
-				if(c == 4) self_base = total + (first - rb[4]); // entry of the home cell's first particle
-				ccount[c] = (re[c] - rb[c]) + (re2[c] - rb2[c]);
-				for(int s = rb[c]; s < re[c]; s++, total++)
+			for(int dz = -1; dz <= 1; dz++) {
+				const int zc = wrap_cell(iz + dz, nz);
+				const int b = cell_start[col + zc], e = cell_start[col + zc + 1];
+				const unsigned code = (unsigned) (c * 3 + dz + 1) << kCodeShift;
+				if(c == 4 && dz == 0) self_base = total;
+				for(int s = b; s < e; s++, total++)
 					if(total < kNbCap) {
-						__pipeline_memcpy_async(&s_stage[total][tid], posf + s, sizeof(float4));
-						s_slot[total][tid] = s;
-					}
-				for(int s = rb2[c]; s < re2[c]; s++, total++)
-					if(total < kNbCap) {
-						__pipeline_memcpy_async(&s_stage[total][tid], posf + s, sizeof(float4));
-						s_slot[total][tid] = s;
+						float *dst = reinterpret_cast<float *>(&s_stage[total][tid]);
+						const float *src = reinterpret_cast<const float *>(posf + s);
+						__pipeline_memcpy_async(dst, src, 8);         // x, y inside the cell
+						__pipeline_memcpy_async(dst + 2, src + 2, 4); // z inside the cell
+						dst[3] = __uint_as_float((unsigned) s | code); // slot and neighbour-cell code
 					}
 			}
-			__pipeline_commit();
 		}
+		__pipeline_commit();
 		const bool staged = total <= kNbCap;
 		__pipeline_wait_prior(0);
 
@@ -108,7 +99,7 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 			const int pick = pr->pick;
 			const int sp = first + pick;
 			tl.tries++;
-			if(!staged) {
+			if(!staged) { // neighbourhood larger than the staging area (dense packing): serial FP64 path
 				trial_serial(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
 				continue;
 			}
@@ -125,45 +116,35 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 			tl.wt += Wfix;
 			const int j_self = self_base + pick;
 			const float4 f_old = s_stage[j_self][tid];
-			const float4 f_new = cell_relative(sc, p_new.x, p_new.y, p_new.z);
+			const float fnx = f_old.x + (float) dx, fny = f_old.y + (float) dy, fnz = f_old.z + (float) dz;
 
 			// ---- 1. FP32 pre-screen over the staged neighbourhood -------------------------
 			int n_cand = 0;
-			{
-				int j = 0;
-#pragma unroll
-				for(int c = 0; c < 9; c++) {
-					// entries of column c: consecutive in the staging order; their x / y offsets are those of the column
-					const float ox = (float) (c / 3 - 1) * wx, oy = (float) (c % 3 - 1) * wy;
-					const float ox_old = ox - f_old.x, oy_old = oy - f_old.y, ox_new = ox - f_new.x, oy_new = oy - f_new.y;
-					for(int k = 0; k < ccount[c]; k++, j++) {
-						if(j == j_self) continue;
-						const float4 q = s_stage[j][tid];
-						int dzc = (int) q.w - iz;
-						dzc -= (dzc > 1) ? nz : 0;
-						dzc += (dzc < -1) ? nz : 0;
-						const float qz = q.z + (float) dzc * wz;
-						const float ax = q.x + ox_old, ay = q.y + oy_old, az = qz - f_old.z;
-						const float bx = q.x + ox_new, by = q.y + oy_new, bz = qz - f_new.z;
-						const float d2o = ax * ax + ay * ay + az * az;
-						const float d2n = bx * bx + by * by + bz * bz;
-						const unsigned flags = (d2o < thr ? kNearOld : 0u) | (d2n < thr ? kNearNew : 0u);
-						if(flags) {
-							if(n_cand < kCandCap) s_cand[n_cand][tid] = (unsigned char) ((unsigned) j | flags);
-							n_cand++;
-						}
-					}
+#pragma unroll 2
+			for(int j = 0; j < total; j++) {
+				if(j == j_self) continue;
+				const float4 q = s_stage[j][tid];
+				const unsigned code = __float_as_uint(q.w) >> kCodeShift;
+				const float qx = q.x + s_off[code][0], qy = q.y + s_off[code][1], qz = q.z + s_off[code][2];
+				const float ax = qx - f_old.x, ay = qy - f_old.y, az = qz - f_old.z;
+				const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
+				const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
+				const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
+				const unsigned flags = (d2o < thr ? kNearOld : 0u) | (d2n < thr ? kNearNew : 0u);
+				if(flags) {
+					if(n_cand < kCandCap) s_cand[n_cand][tid] = (unsigned char) ((unsigned) j | flags);
+					n_cand++;
 				}
 			}
 			tl.checks += 2ull * (unsigned long long) (total - 1);
 			if(n_cand > kCandCap) { // cannot happen for hard spheres with r_cut < 1.5; kept for safety
-				trial_serial(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
 				tl.wt -= Wfix;
 				tl.checks -= 2ull * (unsigned long long) (total - 1);
+				trial_serial(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
 				continue;
 			}
 
-			// ---- 2. FP64 on the candidates, four double positions in flight ------------------
+			// ---- 2. FP64 on the candidates, two double positions in flight -------------------
 			double m[9], mn[9];
 #pragma unroll
 			for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
@@ -173,18 +154,19 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 				for(int j = 0; j < 3; j++) mn[3 * i + j] = dot3_rn(m[3 * i], m[3 * i + 1], m[3 * i + 2], pr->R[j], pr->R[3 + j], pr->R[6 + j]);
 			int b_old = 0, b_new = 0;
 			bool ovl = false;
-			for(int c0 = 0; c0 < n_cand && !ovl; c0 += 4) {
-				double4 q4[4];
-				unsigned e[4];
-				int sq[4];
+#pragma unroll 1
+			for(int c0 = 0; c0 < n_cand && !ovl; c0 += 2) {
+				double4 q4[2];
+				unsigned e[2];
+				int sq[2];
 #pragma unroll
-				for(int k = 0; k < 4; k++) {
+				for(int k = 0; k < 2; k++) {
 					e[k] = (c0 + k < n_cand) ? s_cand[c0 + k][tid] : 0u;
-					sq[k] = s_slot[e[k] & kIdxMask][tid];
+					sq[k] = (int) (__float_as_uint(s_stage[e[k] & kIdxMask][tid].w) & kSlotMask);
 					if(e[k]) q4[k] = pos[sq[k]];
 				}
 #pragma unroll
-				for(int k = 0; k < 4; k++) {
+				for(int k = 0; k < 2; k++) {
 					if(e[k] & kNearNew) {
 						Vec3 d;
 						const double d2 = min_image(sc, p_new, q4[k], d);
@@ -210,8 +192,8 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 				p[0] = p_new.x;
 				p[1] = p_new.y;
 				p[2] = p_new.z;
-				posf[sp] = f_new;
-				s_stage[j_self][tid] = f_new;
+				posf[sp] = cell_relative(sc, p_new.x, p_new.y, p_new.z);
+				s_stage[j_self][tid] = make_float4(fnx, fny, fnz, f_old.w);
 #pragma unroll
 				for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
 				tl.dbonds += b_new - b_old;
@@ -256,14 +238,14 @@ __global__ void __launch_bounds__(kCellThreads, 5) k_sweep_cells(const __grid_co
 	}
 }
 
-int launch_sweep_cells(const SimConst &sc, int colour, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori, Counters *counters,
-		cudaStream_t st) {
-	long long n_active = (long long) (sc.n_side[0] / 2) * (sc.n_side[1] / 2) * (sc.n_side[2] / 2);
-	if(n_active > sc.N) n_active = sc.N;
-	long long blocks = (n_active + kCellThreads - 1) / kCellThreads;
-	if(blocks < 1) blocks = 1;
-	k_sweep_cells<<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, colour, cb.cell_start, cb.work, cb.bins + kWorkStart, proposals, pos, ori, cb.posf,
-			counters);
+// range: device pointer to {first work item, one past the last work item}
+int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
+		double *ori, Counters *counters, cudaStream_t st) {
+	if(max_items < 1) max_items = 1;
+	long long blocks = (max_items + kCellThreads - 1) / kCellThreads;
+	const long long cap = 148ll * 4 * 8; // a few waves of resident blocks; threads stride over the occupancy-sorted list
+	if(blocks > cap) blocks = cap;
+	k_sweep_cells<<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters);
 	return 1;
 }
 

@@ -28,7 +28,8 @@ class Params(C.Structure):
                 ("P", C.c_double), ("rescale_factor_max", C.c_double), ("Lx_move", C.c_int),
                 ("Lx_change_max", C.c_double), ("Lyz_min", C.c_double), ("Lyz_max", C.c_double),
                 ("Lx_reference_sign", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
-                ("lanes_per_cell", C.c_int), ("use_graph", C.c_int), ("shift_every", C.c_int)]
+                ("lanes_per_cell", C.c_int), ("use_graph", C.c_int), ("cells_max_occupancy", C.c_int),
+                ("shift_every", C.c_int)]
 
 
 class Observables(C.Structure):
@@ -112,7 +113,8 @@ class Engine:
 
     def __init__(self, ensemble=NVT, temperature=0.1, disp_max=0.1, theta_max=0.1, kf_delta=0.119, kf_cosmax=0.98,
                  P=0.0, rescale_factor_max=0.0, Lx_move=0, Lx_change_max=0.0, Lyz_min=0.0, Lyz_max=0.0,
-                 Lx_reference_sign=1, seed=12345, device=0, lanes_per_cell=0, use_graph=0, shift_every=0):
+                 Lx_reference_sign=1, seed=12345, device=0, lanes_per_cell=0, use_graph=0, shift_every=0,
+                 cells_max_occupancy=-1):
         self.L = load_library()
         p = Params()
         self.L.pp_default_params(C.byref(p))
@@ -121,6 +123,7 @@ class Engine:
         p.Lx_move, p.Lx_change_max, p.Lyz_min, p.Lyz_max = Lx_move, Lx_change_max, Lyz_min, Lyz_max
         p.Lx_reference_sign, p.seed, p.device = Lx_reference_sign, seed, device
         p.lanes_per_cell, p.use_graph, p.shift_every = lanes_per_cell, use_graph, shift_every
+        p.cells_max_occupancy = cells_max_occupancy
         self.params = p
         self.h = C.c_void_p()
         rc = self.L.pp_create(C.byref(p), C.byref(self.h))

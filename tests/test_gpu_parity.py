@@ -119,7 +119,7 @@ def test_total_bonds_vs_port(pp, oracle, N, rho, delta, cosmax):
     e.close()
 
 
-@pytest.mark.parametrize("lanes", [1, 4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [0, 1, 4, 8, 16, 32])
 def test_sweep_matches_port(pp, oracle, lanes):
     """The CUDA sweep and the serial restatement of the same algorithm give the same trajectory."""
     g = load_golden("gen2000_rho0.5")

@@ -1,9 +1,9 @@
 #!/bin/bash
 # quick scan of the sweep-kernel tile width on two workloads (runs under gpurun)
 for w in 64k 1M; do
-  for l in 1 8 16 32; do
+  for l in 0 1 8 16; do
     steps=400; [ $w = 1M ] && steps=60
-    python bench.py --workload $w --lanes $l --steps $steps --warmup 5 --no-cpu-baseline --e2e-steps 3 | python -c "
+    python bench.py --workload $w --lanes $l --steps $steps --warmup 5 --no-cpu-baseline --e2e-steps 3 --relax-sweeps 200 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 k=d['kernels']
