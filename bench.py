@@ -43,7 +43,7 @@ CELLS_BYTES_PER_PARTICLE = 72
 BONDS_BYTES_PER_PARTICLE = 32
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 # dram__bytes_read.sum + dram__bytes_write.sum per k_sweep_pass launch from the committed ncu captures (profiles/)
-SWEEP_TRAFFIC_BYTES = {}
+SWEEP_TRAFFIC_BYTES = {"64k": 5095520}  # profiles/r01d_sweep_full.txt (L2 flushed before each step)
 
 
 def workload_name(w):

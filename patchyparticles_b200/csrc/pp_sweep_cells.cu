@@ -16,7 +16,8 @@
 //                 is a candidate when its FP32 squared distance is below r_cut^2 + 1e-3 (the FP32
 //                 error is < 1e-5, so no pair the FP64 test would put inside the shell, or flag as
 //                 overlapping, is ever dropped);
-//              2. FP64, reference operation order, on the candidates only (their double positions
+//              2. FP32 orientation screen of the pairs in range (own matrix only), then
+//              3. FP64, reference operation order, on the candidates only (their double positions
 //                 are fetched two at a time): overlap of the new position (MC.c:240), shell test
 //                 (MC.c:241), orientation tests (MC.c:249-261);
 //              3. Metropolis rule (MC.c:332), write-back of position, orientation, FP32 shadow.
@@ -33,6 +34,17 @@ constexpr float kScreenBand = 1e-3f;         // FP32 safety band around r_cut^2
 constexpr unsigned kNearOld = 0x40u, kNearNew = 0x80u, kIdxMask = 0x3fu;
 constexpr int kCodeShift = 26;               // staged tag: slot | neighbour-cell code << 26
 constexpr unsigned kSlotMask = (1u << kCodeShift) - 1u;
+
+// May one of the four patches of the particle with (FP32) matrix mf point at a neighbour at separation
+// (x, y, z), |.|^2 = d2 ?  d . (M b_i) = (M^T d) . b_i with b_i = (+-1, +-1, +-1) * base_z (system.c:23-31);
+// only the largest projection matters.  false means "certainly not" (see the band in the caller).
+__device__ __forceinline__ bool may_point(const float *mf, float x, float y, float z, float d2, float point_thr) {
+	const float ux = fmaf(mf[6], z, fmaf(mf[3], y, mf[0] * x));
+	const float uy = fmaf(mf[7], z, fmaf(mf[4], y, mf[1] * x));
+	const float uz = fmaf(mf[8], z, fmaf(mf[5], y, mf[2] * x));
+	const float pm = fmaxf(fmaxf(uz - ux - uy, ux - uy - uz), fmaxf(ux + uy + uz, uy - ux - uz));
+	return point_thr < 0.f || (pm > 0.f && pm * pm >= point_thr * d2);
+}
 
 struct CellBlockCounters {
 	unsigned int tries, accepted, confined, overlapped;
@@ -59,6 +71,9 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 	const int w_begin = range[0], w_end = range[1];
 	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
 	const float thr = (float) sc.sqr_rcut + kScreenBand;
+	const float core_lo = 1.f - kScreenBand, core_hi = 1.f + kScreenBand; // certain overlap below, certain clearance above
+	// (M^T d . b_i)^2 > cosmax^2 d^2 / base_z^2 with a 1e-3 relative band; -1 disables the screen (every pair in range goes to FP64)
+	const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - kScreenBand) : -1.f;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0, 0};
 
 	for(int wi = w_begin + blockIdx.x * kCellThreads + tid; wi < w_end; wi += gridDim.x * kCellThreads) {
@@ -105,6 +120,9 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			}
 			const double dx = pr->dx, dy = pr->dy, dz = pr->dz;
 			const double4 p4 = pos[sp];
+			double m[9]; // requested now, needed after the pre-screen: the latency hides behind it
+#pragma unroll
+			for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
 			const Vec3 p_old = {p4.x, p4.y, p4.z};
 			const Vec3 p_new = {__dadd_rn(p4.x, dx), __dadd_rn(p4.y, dy), __dadd_rn(p4.z, dz)};
 			int cx, cy, cz;
@@ -118,8 +136,9 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			const float4 f_old = s_stage[j_self][tid];
 			const float fnx = f_old.x + (float) dx, fny = f_old.y + (float) dy, fnz = f_old.z + (float) dz;
 
-			// ---- 1. FP32 pre-screen over the staged neighbourhood -------------------------
+			// ---- 1. FP32 distance screen over the staged neighbourhood ---------------------
 			int n_cand = 0;
+			bool ovl = false;
 #pragma unroll 2
 			for(int j = 0; j < total; j++) {
 				if(j == j_self) continue;
@@ -130,6 +149,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
 				const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
 				const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
+				ovl |= d2n < core_lo;
 				const unsigned flags = (d2o < thr ? kNearOld : 0u) | (d2n < thr ? kNearNew : 0u);
 				if(flags) {
 					if(n_cand < kCandCap) s_cand[n_cand][tid] = (unsigned char) ((unsigned) j | flags);
@@ -137,6 +157,10 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				}
 			}
 			tl.checks += 2ull * (unsigned long long) (total - 1);
+			if(ovl) { // overlapping beyond any FP32 doubt: rejected whatever the bonds (MC.c:296-299, 332)
+				tl.ovl++;
+				continue;
+			}
 			if(n_cand > kCandCap) { // cannot happen for hard spheres with r_cut < 1.5; kept for safety
 				tl.wt -= Wfix;
 				tl.checks -= 2ull * (unsigned long long) (total - 1);
@@ -144,40 +168,62 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				continue;
 			}
 
-			// ---- 2. FP64 on the candidates, two double positions in flight -------------------
-			double m[9], mn[9];
-#pragma unroll
-			for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
+			// ---- 2. FP32 orientation screen of the pairs in range -------------------------------
+			// A bond needs one of the moved particle's patches to point at the neighbour (MC.c:249-255).
+			// With cosmax = 0.98 that is true for ~4 % of the pairs in the shell; the others are dismissed
+			// here from the FP32 separation and the FP32 copy of the particle's own matrix, through a
+			// relative band of 1e-3 on the squared cosine (the FP32 error is < 1e-5).  What survives --
+			// pointing or doubtful patches, separations within the band of the hard core -- goes to FP64.
+			double mn[9];
 #pragma unroll
 			for(int i = 0; i < 3; i++)
 #pragma unroll
 				for(int j = 0; j < 3; j++) mn[3 * i + j] = dot3_rn(m[3 * i], m[3 * i + 1], m[3 * i + 2], pr->R[j], pr->R[3 + j], pr->R[6 + j]);
-			int b_old = 0, b_new = 0;
-			bool ovl = false;
-#pragma unroll 1
-			for(int c0 = 0; c0 < n_cand && !ovl; c0 += 2) {
-				double4 q4[2];
-				unsigned e[2];
-				int sq[2];
+			int n_exact = 0;
+			{
+				float mf[9], mnf[9];
 #pragma unroll
-				for(int k = 0; k < 2; k++) {
-					e[k] = (c0 + k < n_cand) ? s_cand[c0 + k][tid] : 0u;
-					sq[k] = (int) (__float_as_uint(s_stage[e[k] & kIdxMask][tid].w) & kSlotMask);
-					if(e[k]) q4[k] = pos[sq[k]];
+				for(int k = 0; k < 9; k++) {
+					mf[k] = (float) m[k];
+					mnf[k] = (float) mn[k];
 				}
-#pragma unroll
-				for(int k = 0; k < 2; k++) {
-					if(e[k] & kNearNew) {
-						Vec3 d;
-						const double d2 = min_image(sc, p_new, q4[k], d);
-						if(d2 < 1.) ovl = true;
-						else if(d2 < sc.sqr_rcut) b_new += patches_bond_m(sc, d, d2, mn, ori + 9ll * sq[k]) ? 1 : 0;
+				for(int c0 = 0; c0 < n_cand; c0++) {
+					const unsigned e = s_cand[c0][tid];
+					const float4 q = s_stage[e & kIdxMask][tid];
+					const unsigned code = __float_as_uint(q.w) >> kCodeShift;
+					const float qx = q.x + s_off[code][0], qy = q.y + s_off[code][1], qz = q.z + s_off[code][2];
+					unsigned keep = 0u;
+					if(e & kNearNew) {
+						const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
+						const float d2 = fmaf(bz, bz, fmaf(by, by, bx * bx));
+						if(d2 < core_hi || may_point(mnf, bx, by, bz, d2, point_thr)) keep |= kNearNew;
 					}
-					if(e[k] & kNearOld) {
-						Vec3 d;
-						const double d2 = min_image(sc, p_old, q4[k], d);
-						if(d2 >= 1. && d2 < sc.sqr_rcut) b_old += patches_bond_m(sc, d, d2, m, ori + 9ll * sq[k]) ? 1 : 0;
+					if(e & kNearOld) {
+						const float ax = qx - f_old.x, ay = qy - f_old.y, az = qz - f_old.z;
+						const float d2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+						if(may_point(mf, ax, ay, az, d2, point_thr)) keep |= kNearOld;
 					}
+					if(keep) s_cand[n_exact++][tid] = (unsigned char) ((e & kIdxMask) | keep); // in place: n_exact <= c0
+				}
+			}
+
+			// ---- 3. FP64, reference operation order, on what is left ---------------------------
+			int b_old = 0, b_new = 0;
+#pragma unroll 1
+			for(int c0 = 0; c0 < n_exact && !ovl; c0++) {
+				const unsigned e = s_cand[c0][tid];
+				const int sq = (int) (__float_as_uint(s_stage[e & kIdxMask][tid].w) & kSlotMask);
+				const double4 q4 = pos[sq];
+				if(e & kNearNew) {
+					Vec3 d;
+					const double d2 = min_image(sc, p_new, q4, d);
+					if(d2 < 1.) ovl = true;
+					else if(d2 < sc.sqr_rcut) b_new += patches_bond_m(sc, d, d2, mn, ori + 9ll * sq) ? 1 : 0;
+				}
+				if(e & kNearOld) {
+					Vec3 d;
+					const double d2 = min_image(sc, p_old, q4, d);
+					if(d2 >= 1. && d2 < sc.sqr_rcut) b_old += patches_bond_m(sc, d, d2, m, ori + 9ll * sq) ? 1 : 0;
 				}
 			}
 			if(ovl) { // hard-core overlap: rejected whatever the bonds (MC.c:296-299, 332)
