@@ -139,31 +139,39 @@ __device__ __forceinline__ int work_bin(const SimConst &sc, int ix, int iy, int 
 	return colour * kWorkBuckets + (kWorkBuckets - bucket);                         // big cells first
 }
 
-// per cell: order its particles by id (insertion sort; a handful of particles), choose and count its work bin
+// per cell: order its particles by id (insertion sort; a handful of particles), choose and count its work bin.
+// The bins are few and hot: they are counted per block in shared memory, one global atomic per bin and block.
 __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start, int *__restrict__ perm,
 		const int *__restrict__ pid_src, int *__restrict__ bin_count, int *__restrict__ cell_bin, int cells_max_occupancy, int cells_nb_cap) {
+	__shared__ int s_bin[8 * kWorkBuckets];
+	if(threadIdx.x < 8 * kWorkBuckets) s_bin[threadIdx.x] = 0;
+	__syncthreads();
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= sc.n_cells) return;
-	const int b = cell_start[c], e = cell_start[c + 1];
-	if(e == b) return;
-	const int nyz = sc.n_side[1] * sc.n_side[2];
-	const int ix = c / nyz, iy = (c - ix * nyz) / sc.n_side[2], iz = c - ix * nyz - iy * sc.n_side[2];
-	const bool owned = ix >= sc.own_lo && ix < sc.own_hi;
-	for(int a = b + 1; a < e; a++) {
-		const int src = perm[a];
-		const int key = pid_src[src];
-		int k = a - 1;
-		while(k >= b && pid_src[perm[k]] > key) {
-			perm[k + 1] = perm[k];
-			k--;
+	if(c < sc.n_cells) {
+		const int b = cell_start[c], e = cell_start[c + 1];
+		if(e > b) {
+			const int nyz = sc.n_side[1] * sc.n_side[2];
+			const int ix = c / nyz, iy = (c - ix * nyz) / sc.n_side[2], iz = c - ix * nyz - iy * sc.n_side[2];
+			for(int a = b + 1; a < e; a++) {
+				const int src = perm[a];
+				const int key = pid_src[src];
+				int k = a - 1;
+				while(k >= b && pid_src[perm[k]] > key) {
+					perm[k + 1] = perm[k];
+					k--;
+				}
+				perm[k + 1] = src;
+			}
+			if(ix >= sc.own_lo && ix < sc.own_hi) { // halo cells are never moved here
+				const bool dense = (e - b <= cells_max_occupancy) && neighbourhood_total(sc, cell_start, ix, iy, iz) > cells_nb_cap;
+				const int bin = work_bin(sc, ix, iy, iz, e - b, dense);
+				cell_bin[c] = bin;
+				atomicAdd(&s_bin[bin], 1);
+			}
 		}
-		perm[k + 1] = src;
 	}
-	if(!owned) return; // halo cells are never moved here
-	const bool dense = (e - b <= cells_max_occupancy) && neighbourhood_total(sc, cell_start, ix, iy, iz) > cells_nb_cap;
-	const int bin = work_bin(sc, ix, iy, iz, e - b, dense);
-	cell_bin[c] = bin;
-	atomicAdd(bin_count + bin, 1);
+	__syncthreads();
+	if(threadIdx.x < 8 * kWorkBuckets && s_bin[threadIdx.x]) atomicAdd(bin_count + threadIdx.x, s_bin[threadIdx.x]);
 }
 
 // one warp: exclusive scan of the 8 * kWorkBuckets bins; work_start[colour] marks the colour boundaries
@@ -189,15 +197,27 @@ __global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__
 	}
 }
 
+// work lists: rank inside the block's share of a bin from shared memory, one global atomic per bin and block
 __global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
 		const int *__restrict__ bin_start, int *__restrict__ bin_fill, const int *__restrict__ cell_bin, int *__restrict__ work) {
+	__shared__ int s_cnt[8 * kWorkBuckets], s_base[8 * kWorkBuckets];
+	if(threadIdx.x < 8 * kWorkBuckets) s_cnt[threadIdx.x] = 0;
+	__syncthreads();
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= sc.n_cells) return;
-	const int n = cell_start[c + 1] - cell_start[c];
-	const int layer = c / (sc.n_side[1] * sc.n_side[2]);
-	if(n == 0 || layer < sc.own_lo || layer >= sc.own_hi) return;
-	const int bin = cell_bin[c];
-	work[bin_start[bin] + atomicAdd(bin_fill + bin, 1)] = c;
+	int bin = -1, rank = 0;
+	if(c < sc.n_cells) {
+		const int n = cell_start[c + 1] - cell_start[c];
+		const int layer = c / (sc.n_side[1] * sc.n_side[2]);
+		if(n > 0 && layer >= sc.own_lo && layer < sc.own_hi) {
+			bin = cell_bin[c];
+			rank = atomicAdd(&s_cnt[bin], 1);
+		}
+	}
+	__syncthreads();
+	if(threadIdx.x < 8 * kWorkBuckets && s_cnt[threadIdx.x])
+		s_base[threadIdx.x] = bin_start[threadIdx.x] + atomicAdd(bin_fill + threadIdx.x, s_cnt[threadIdx.x]);
+	__syncthreads();
+	if(bin >= 0) work[s_base[bin] + rank] = c;
 }
 
 __global__ void __launch_bounds__(256) k_cell_gather_pos(const __grid_constant__ SimConst sc, const int *__restrict__ perm,

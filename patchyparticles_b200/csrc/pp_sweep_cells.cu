@@ -46,6 +46,8 @@ __device__ __forceinline__ bool may_point(const float *mf, float x, float y, flo
 	return point_thr < 0.f || (pm > 0.f && pm * pm >= point_thr * d2);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct CellBlockCounters {
 	unsigned int tries, accepted, confined, overlapped;
 	int dbonds;
@@ -81,6 +83,12 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 		const int ix = cell / nyz, iy = (cell - ix * nyz) / nz, iz = cell - ix * nyz - iy * nz;
 		const int first = cell_start[cell];
 		const int n_here = cell_start[cell + 1] - first;
+		for(int t = 0; t < n_here; t++) { // the cell's own trials: on their way to L2 while the neighbourhood is staged
+			prefetch_l2(proposals + first + t);
+			prefetch_l2(pos + first + t);
+			prefetch_l2(ori + 9ll * (first + t));
+			prefetch_l2(ori + 9ll * (first + t) + 8);
+		}
 
 		// ---- stage the 27-cell neighbourhood: all copies in flight, one wait ------------------------------
 		int total = 0, self_base = 0;
