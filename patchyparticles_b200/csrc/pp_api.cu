@@ -201,7 +201,7 @@ int ensure_state(pp_handle *h, size_t n) {
 	CUDA_OK(h, cudaMalloc(&h->cb.cell_of, cap * sizeof(int)));
 	CUDA_OK(h, cudaMalloc(&h->cb.perm, cap * sizeof(int)));
 	CUDA_OK(h, cudaMalloc(&h->cb.cell_sorted, cap * sizeof(int)));
-	CUDA_OK(h, cudaMalloc(&h->cb.posf, cap * sizeof(float4)));
+	CUDA_OK(h, cudaMalloc(&h->cb.posf, cap * sizeof(uint2)));
 	CUDA_OK(h, cudaMalloc(&h->d_proposals, cap * sizeof(Proposal)));
 	CUDA_OK(h, cudaMalloc(&h->d_stage_r, cap * 3 * sizeof(double)));
 	CUDA_OK(h, cudaMalloc(&h->d_stage_o, cap * 9 * sizeof(double)));

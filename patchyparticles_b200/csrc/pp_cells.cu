@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ Si
 
 __global__ void __launch_bounds__(256) k_cell_gather_pos(const __grid_constant__ SimConst sc, const int *__restrict__ perm,
 		const int *__restrict__ cell_of, const double4 *__restrict__ pos_src, const int *__restrict__ pid_src, double4 *__restrict__ pos_dst,
-		int *__restrict__ pid_dst, int *__restrict__ slot_of, int *__restrict__ cell_sorted, float4 *__restrict__ posf) {
+		int *__restrict__ pid_dst, int *__restrict__ slot_of, int *__restrict__ cell_sorted, const int *__restrict__ cell_start,
+		uint2 *__restrict__ posf) {
 	const int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if(s >= sc.N) return;
 	const int src = perm[s];
@@ -231,8 +232,9 @@ __global__ void __launch_bounds__(256) k_cell_gather_pos(const __grid_constant__
 	const int id = pid_src[src];
 	pid_dst[s] = id;
 	slot_of[id] = s;
-	cell_sorted[s] = cell_of[src];
-	posf[s] = cell_relative(sc, p.x, p.y, p.z); // FP32 shadow used by the sweep's distance pre-screen
+	const int c = cell_of[src];
+	cell_sorted[s] = c;
+	posf[s] = cell_shadow(sc, p.x, p.y, p.z, s - cell_start[c]); // shadow used by the sweep's pre-screens
 }
 
 __global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int *__restrict__ perm, const double *__restrict__ ori_src,
@@ -265,7 +267,7 @@ int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView
 	k_cell_order<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.perm, src.pid, cb.bins + kBinCount, cb.cell_fill, cells_max_occupancy, kCellsNbCap);
 	k_bins_scan<<<1, 160, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkRanges, cells_max_occupancy);
 	k_work_scatter<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.bins + kBinStart, cb.bins + kBinFill, cb.cell_fill, cb.work);
-	k_cell_gather_pos<<<nb, 256, 0, st>>>(sc, cb.perm, cb.cell_of, src.pos, src.pid, dst.pos, dst.pid, slot_of, cb.cell_sorted, cb.posf);
+	k_cell_gather_pos<<<nb, 256, 0, st>>>(sc, cb.perm, cb.cell_of, src.pos, src.pid, dst.pos, dst.pid, slot_of, cb.cell_sorted, cb.cell_start, cb.posf);
 	const long long n9 = 9ll * N;
 	k_cell_gather_ori<<<(unsigned) ((n9 + 255) / 256), 256, 0, st>>>(n9, cb.perm, src.ori, dst.ori);
 	return 10;

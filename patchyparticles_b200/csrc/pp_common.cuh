@@ -112,33 +112,22 @@ __device__ __forceinline__ int global_cell(const SimConst &sc, int ix, int iy, i
 	return (gx * sc.n_side[1] + iy) * sc.n_side[2] + iz;
 }
 
-// FP32 shadow of a position: offset inside its cell along x, y, z and the cell's z index.  Only the
-// sweep's distance pre-screen reads it (with a 1e-3 safety band); every decision is taken in FP64.
-__device__ __forceinline__ float4 cell_relative(const SimConst &sc, double x, double y, double z) {
-	float4 out;
-	{
-		const double t = __dmul_rn(__dsub_rn(x, sc.shift[0]), sc.inv_box[0]);
-		const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) sc.n_side[0]);
-		int c = (int) g;
-		c = c < sc.n_side[0] ? c : sc.n_side[0] - 1;
-		out.x = (float) ((g - (double) c) * sc.cell_w[0]);
-	}
-	{
-		const double t = __dmul_rn(__dsub_rn(y, sc.shift[1]), sc.inv_box[1]);
-		const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) sc.n_side[1]);
-		int c = (int) g;
-		c = c < sc.n_side[1] ? c : sc.n_side[1] - 1;
-		out.y = (float) ((g - (double) c) * sc.cell_w[1]);
-	}
-	{
-		const double t = __dmul_rn(__dsub_rn(z, sc.shift[2]), sc.inv_box[2]);
-		const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) sc.n_side[2]);
-		int c = (int) g;
-		c = c < sc.n_side[2] ? c : sc.n_side[2] - 1;
-		out.z = (float) ((g - (double) c) * sc.cell_w[2]);
-		out.w = (float) c;
-	}
-	return out;
+// Fixed-point shadow of a position: offset inside its cell along x, y, z in units of cell_w / 65535
+// (16 bits each) and the particle's rank inside its cell.  Only the conservative FP32 pre-screens of
+// the thread-per-cell sweep kernel read it (quantisation + FP32 error of a squared separation
+// < 2e-4, screen bands 2e-3); every decision is taken in FP64.
+__device__ __forceinline__ unsigned shadow_coord(double r, double shift, double inv_box, int n_side) {
+	const double t = __dmul_rn(__dsub_rn(r, shift), inv_box);
+	const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) n_side);
+	int c = (int) g;
+	c = c < n_side ? c : n_side - 1;
+	return __double2uint_rn((g - (double) c) * 65535.0); // 0 .. 65535
+}
+__device__ __forceinline__ uint2 cell_shadow(const SimConst &sc, double x, double y, double z, int rank) {
+	const unsigned qx = shadow_coord(x, sc.shift[0], sc.inv_box[0], sc.n_side[0]);
+	const unsigned qy = shadow_coord(y, sc.shift[1], sc.inv_box[1], sc.n_side[1]);
+	const unsigned qz = shadow_coord(z, sc.shift[2], sc.inv_box[2], sc.n_side[2]);
+	return make_uint2(qx | (qy << 16), qz | ((unsigned) rank << 16));
 }
 
 // rint(d / box) as the reference computes it (MC.c:234-236), without the division in the common

@@ -14,7 +14,7 @@ struct StateView {
 
 // work lists of the sweep: 8 colours x kWorkBuckets occupancy buckets (descending occupancy)
 constexpr int kWorkBuckets = 16;
-constexpr int kCellsNbCap = 32; // neighbours the thread-per-cell sweep kernel can stage; cells with more go to the tile kernel
+constexpr int kCellsNbCap = 48; // neighbours the thread-per-cell sweep kernel can stage; cells with more go to the tile kernel
 constexpr int kBinCount = 0;                              // [8 * kWorkBuckets] cells per bin
 constexpr int kBinStart = 8 * kWorkBuckets;               // [8 * kWorkBuckets + 1] exclusive prefix
 constexpr int kBinFill = kBinStart + 8 * kWorkBuckets + 1; // [8 * kWorkBuckets] scatter cursors
@@ -31,7 +31,7 @@ struct CellBuffers {
 	int *perm;        // N
 	int *work;        // n_cells: non-empty cells grouped by colour, occupancy descending
 	int *bins;        // kBinInts
-	float4 *posf;     // N: position inside its cell (x, y, z) and the cell's z index, FP32 (pre-screen only)
+	uint2 *posf;      // N: 16-bit fixed-point position inside its cell (x, y, z) + rank in the cell (pre-screens only)
 };
 
 // A pre-generated roto-translation proposal (MC.c:312-324): rotation matrix R (new = old . R),

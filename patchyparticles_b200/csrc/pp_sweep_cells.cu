@@ -9,18 +9,19 @@
 // the tile kernel, both running concurrently on two streams.  The work list hands consecutive
 // threads cells of equal occupancy, which keeps the lanes of a warp in the same trial.
 //
-//   per cell   the FP32 shadow positions (float4: offset inside the cell + the cell's z index) of the
-//              27-cell neighbourhood are brought into shared memory with cp.async -- all copies in
-//              flight at once, one wait; each entry is tagged with its slot and its neighbour-cell code;
-//   per trial  1. FP32 pre-screen of the staged neighbours for the old and the new position; a pair
-//                 is a candidate when its FP32 squared distance is below r_cut^2 + 1e-3 (the FP32
-//                 error is < 1e-5, so no pair the FP64 test would put inside the shell, or flag as
-//                 overlapping, is ever dropped);
-//              2. FP32 orientation screen of the pairs in range (own matrix only), then
-//              3. FP64, reference operation order, on the candidates only (their double positions
-//                 are fetched two at a time): overlap of the new position (MC.c:240), shell test
-//                 (MC.c:241), orientation tests (MC.c:249-261);
-//              3. Metropolis rule (MC.c:332), write-back of position, orientation, FP32 shadow.
+//   per cell   the shadow positions (8 bytes: 16-bit fixed-point offset inside the cell + rank in the
+//              cell) of the 27-cell neighbourhood are brought into shared memory with cp.async -- all
+//              copies in flight at once, one wait; each entry is tagged with its neighbour-cell code;
+//   per trial  1. FP32 distance screen of the staged neighbours for the old and the new position: a
+//                 new position closer than 1 - 2e-3 (squared) to a neighbour is rejected on the spot,
+//                 a pair is a candidate when its squared distance is below r_cut^2 + 2e-3 (the
+//                 shadow arithmetic is good to 2e-4, so no pair the FP64 test would put inside the
+//                 shell, or flag as overlapping, is ever dropped);
+//              2. FP32 orientation screen of the candidates (own matrix only): most pairs in the
+//                 shell cannot bond because no patch of the moved particle points at them;
+//              3. FP64, reference operation order, on what is left: overlap of the new position
+//                 (MC.c:240), shell test (MC.c:241), orientation tests (MC.c:249-261);
+//              4. Metropolis rule (MC.c:332), write-back of position, orientation, shadow.
 #include "pp_trial_serial.cuh"
 
 #include <cuda_pipeline.h>
@@ -30,10 +31,13 @@ namespace pp {
 constexpr int kCellThreads = 64;
 constexpr int kNbCap = kCellsNbCap;          // staged neighbours per cell; the cell build routes denser cells to the tile kernel
 constexpr int kCandCap = kCellsNbCap;        // candidates per trial (at most one entry per neighbour)
-constexpr float kScreenBand = 1e-3f;         // FP32 safety band around r_cut^2
+constexpr float kScreenBand = 2e-3f;         // safety band of the FP32 screens (error of the shadow arithmetic < 2e-4)
 constexpr unsigned kNearOld = 0x40u, kNearNew = 0x80u, kIdxMask = 0x3fu;
-constexpr int kCodeShift = 26;               // staged tag: slot | neighbour-cell code << 26
-constexpr unsigned kSlotMask = (1u << kCodeShift) - 1u;
+static_assert(kNbCap <= 64, "candidate entries index the staging area with 6 bits");
+
+// A 16-bit shadow coordinate q as the float 2^23 + q (one PRMT); the caller folds the 2^23 into its FMA.
+__device__ __forceinline__ float shadow_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
+__device__ __forceinline__ float shadow_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
 // May one of the four patches of the particle with (FP32) matrix mf point at a neighbour at separation
 // (x, y, z), |.|^2 = d2 ?  d . (M b_i) = (M^T d) . b_i with b_i = (+-1, +-1, +-1) * base_z (system.c:23-31);
@@ -56,17 +60,19 @@ struct CellBlockCounters {
 
 __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
-		float4 *posf, Counters *__restrict__ counters) {
-	__shared__ __align__(16) float4 s_stage[kNbCap][kCellThreads]; // [entry][thread]: conflict-free 16-byte accesses
+		uint2 *posf, Counters *__restrict__ counters) {
+	__shared__ __align__(8) uint2 s_stage[kNbCap][kCellThreads]; // [entry][thread]: shadow of a staged neighbour
+	__shared__ unsigned char s_tag[kNbCap][kCellThreads];       // its neighbour-cell code, 0 .. 26
 	__shared__ unsigned char s_cand[kCandCap][kCellThreads];
-	__shared__ float s_off[27][3]; // offset of neighbour cell `code` from the home cell
+	__shared__ float s_off[27][3]; // offset of neighbour cell `code` from the home cell, minus 2^23 shadow units
 	__shared__ CellBlockCounters s_cnt;
 	const int tid = threadIdx.x;
 	if(tid == 0) s_cnt = CellBlockCounters{0, 0, 0, 0, 0, 0, 0, 0};
+	const float ux = (float) (sc.cell_w[0] / 65535.), uy = (float) (sc.cell_w[1] / 65535.), uz = (float) (sc.cell_w[2] / 65535.); // shadow units
 	if(tid < 27) {
-		s_off[tid][0] = (float) (tid / 9 - 1) * (float) sc.cell_w[0];
-		s_off[tid][1] = (float) ((tid / 3) % 3 - 1) * (float) sc.cell_w[1];
-		s_off[tid][2] = (float) (tid % 3 - 1) * (float) sc.cell_w[2];
+		s_off[tid][0] = (float) ((double) (tid / 9 - 1) * sc.cell_w[0] - 8388608. * (double) ux);
+		s_off[tid][1] = (float) ((double) ((tid / 3) % 3 - 1) * sc.cell_w[1] - 8388608. * (double) uy);
+		s_off[tid][2] = (float) ((double) (tid % 3 - 1) * sc.cell_w[2] - 8388608. * (double) uz);
 	}
 	__syncthreads();
 
@@ -101,15 +107,11 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			for(int dz = -1; dz <= 1; dz++) {
 				const int zc = wrap_cell(iz + dz, nz);
 				const int b = cell_start[col + zc], e = cell_start[col + zc + 1];
-				const unsigned code = (unsigned) (c * 3 + dz + 1) << kCodeShift;
 				if(c == 4 && dz == 0) self_base = total;
 				for(int s = b; s < e; s++, total++)
 					if(total < kNbCap) {
-						float *dst = reinterpret_cast<float *>(&s_stage[total][tid]);
-						const float *src = reinterpret_cast<const float *>(posf + s);
-						__pipeline_memcpy_async(dst, src, 8);         // x, y inside the cell
-						__pipeline_memcpy_async(dst + 2, src + 2, 4); // z inside the cell
-						dst[3] = __uint_as_float((unsigned) s | code); // slot and neighbour-cell code
+						__pipeline_memcpy_async(&s_stage[total][tid], posf + s, 8);
+						s_tag[total][tid] = (unsigned char) (c * 3 + dz + 1);
 					}
 			}
 		}
@@ -141,8 +143,10 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			const unsigned long long Wfix = (unsigned long long) pr->wfix;
 			tl.wt += Wfix;
 			const int j_self = self_base + pick;
-			const float4 f_old = s_stage[j_self][tid];
-			const float fnx = f_old.x + (float) dx, fny = f_old.y + (float) dy, fnz = f_old.z + (float) dz;
+			const uint2 own = s_stage[j_self][tid];
+			const float fox = fmaf(shadow_lo(own.x), ux, s_off[13][0]), foy = fmaf(shadow_hi(own.x), uy, s_off[13][1]),
+					foz = fmaf(shadow_lo(own.y), uz, s_off[13][2]);
+			const float fnx = fox + (float) dx, fny = foy + (float) dy, fnz = foz + (float) dz;
 
 			// ---- 1. FP32 distance screen over the staged neighbourhood ---------------------
 			int n_cand = 0;
@@ -150,10 +154,11 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 #pragma unroll 2
 			for(int j = 0; j < total; j++) {
 				if(j == j_self) continue;
-				const float4 q = s_stage[j][tid];
-				const unsigned code = __float_as_uint(q.w) >> kCodeShift;
-				const float qx = q.x + s_off[code][0], qy = q.y + s_off[code][1], qz = q.z + s_off[code][2];
-				const float ax = qx - f_old.x, ay = qy - f_old.y, az = qz - f_old.z;
+				const uint2 q = s_stage[j][tid];
+				const unsigned code = s_tag[j][tid];
+				const float qx = fmaf(shadow_lo(q.x), ux, s_off[code][0]), qy = fmaf(shadow_hi(q.x), uy, s_off[code][1]),
+						qz = fmaf(shadow_lo(q.y), uz, s_off[code][2]);
+				const float ax = qx - fox, ay = qy - foy, az = qz - foz;
 				const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
 				const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
 				const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
@@ -197,9 +202,10 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				}
 				for(int c0 = 0; c0 < n_cand; c0++) {
 					const unsigned e = s_cand[c0][tid];
-					const float4 q = s_stage[e & kIdxMask][tid];
-					const unsigned code = __float_as_uint(q.w) >> kCodeShift;
-					const float qx = q.x + s_off[code][0], qy = q.y + s_off[code][1], qz = q.z + s_off[code][2];
+					const uint2 q = s_stage[e & kIdxMask][tid];
+					const unsigned code = s_tag[e & kIdxMask][tid];
+					const float qx = fmaf(shadow_lo(q.x), ux, s_off[code][0]), qy = fmaf(shadow_hi(q.x), uy, s_off[code][1]),
+							qz = fmaf(shadow_lo(q.y), uz, s_off[code][2]);
 					unsigned keep = 0u;
 					if(e & kNearNew) {
 						const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 						if(d2 < core_hi || may_point(mnf, bx, by, bz, d2, point_thr)) keep |= kNearNew;
 					}
 					if(e & kNearOld) {
-						const float ax = qx - f_old.x, ay = qy - f_old.y, az = qz - f_old.z;
+						const float ax = qx - fox, ay = qy - foy, az = qz - foz;
 						const float d2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
 						if(may_point(mf, ax, ay, az, d2, point_thr)) keep |= kNearOld;
 					}
@@ -220,7 +226,11 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 #pragma unroll 1
 			for(int c0 = 0; c0 < n_exact && !ovl; c0++) {
 				const unsigned e = s_cand[c0][tid];
-				const int sq = (int) (__float_as_uint(s_stage[e & kIdxMask][tid].w) & kSlotMask);
+				const int code = s_tag[e & kIdxMask][tid], c9 = code / 3; // slot = first of its cell + rank
+				int ncx = ix + c9 / 3 - 1;
+				if(!sc.slab) ncx = wrap_cell(ncx, sc.nxl);
+				const int ncell = (ncx * ny + wrap_cell(iy + c9 % 3 - 1, ny)) * nz + wrap_cell(iz + code - 3 * c9 - 1, nz);
+				const int sq = cell_start[ncell] + (int) (s_stage[e & kIdxMask][tid].y >> 16);
 				const double4 q4 = pos[sq];
 				if(e & kNearNew) {
 					Vec3 d;
@@ -246,8 +256,9 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				p[0] = p_new.x;
 				p[1] = p_new.y;
 				p[2] = p_new.z;
-				posf[sp] = cell_relative(sc, p_new.x, p_new.y, p_new.z);
-				s_stage[j_self][tid] = make_float4(fnx, fny, fnz, f_old.w);
+				const uint2 moved = cell_shadow(sc, p_new.x, p_new.y, p_new.z, pick);
+				posf[sp] = moved;
+				s_stage[j_self][tid] = moved;
 #pragma unroll
 				for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
 				tl.dbonds += b_new - b_old;

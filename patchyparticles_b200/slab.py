@@ -58,7 +58,7 @@ class _DeviceBuffer:
 def device_view(ptr, n, dtype, device):
     if n == 0:
         return torch.empty(0, dtype=dtype, device=device)
-    typestr = {torch.float64: "<f8", torch.float32: "<f4"}[dtype]
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4"}[dtype]
     return torch.as_tensor(_DeviceBuffer(ptr, n, typestr), device=device)
 
 
@@ -146,9 +146,9 @@ class SlabEngine:
         rp, ro, rf, nr = e.slab_halo(1 - send_side, recv=True)
         _dbg(self.rank, "halo refresh side", send_side, "send", ns, "recv", nr)
         send = [device_view(sp, 4 * ns, torch.float64, dev), device_view(so, 9 * ns, torch.float64, dev),
-                device_view(sf, 4 * ns, torch.float32, dev)]
+                device_view(sf, 2 * ns, torch.int32, dev)]
         recv = [device_view(rp, 4 * nr, torch.float64, dev), device_view(ro, 9 * nr, torch.float64, dev),
-                device_view(rf, 4 * nr, torch.float32, dev)]
+                device_view(rf, 2 * nr, torch.int32, dev)]
         if send_side == 0:
             exchange_with_neighbours(self.rank, self.world, send, [], [], recv)
         else:
