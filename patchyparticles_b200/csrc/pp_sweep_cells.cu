@@ -58,21 +58,31 @@ struct CellBlockCounters {
 	unsigned long long w_tries, w_accepted, pair_checks;
 };
 
+// shadow of a staged neighbour -> FP32 position relative to the home cell's origin
+__device__ __forceinline__ void shadow_position(const uint2 q, const float4 off, float ux, float uy, float uz, float &x, float &y, float &z) {
+	x = fmaf(shadow_lo(q.x), ux, off.x);
+	y = fmaf(shadow_hi(q.x), uy, off.y);
+	z = fmaf(shadow_lo(q.y), uz, off.z);
+}
+
+constexpr int kFarCode = 27; // tag of an entry that must not pair with anything: its cell offset is far outside the screens
+
 __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
 		uint2 *posf, Counters *__restrict__ counters) {
 	__shared__ __align__(8) uint2 s_stage[kNbCap][kCellThreads]; // [entry][thread]: shadow of a staged neighbour
 	__shared__ unsigned char s_tag[kNbCap][kCellThreads];       // its neighbour-cell code, 0 .. 26
 	__shared__ unsigned char s_cand[kCandCap][kCellThreads];
-	__shared__ float s_off[27][3]; // offset of neighbour cell `code` from the home cell, minus 2^23 shadow units
+	__shared__ __align__(16) float4 s_off[28]; // offset of neighbour cell `code` from the home cell, minus 2^23 shadow units
 	__shared__ CellBlockCounters s_cnt;
 	const int tid = threadIdx.x;
 	if(tid == 0) s_cnt = CellBlockCounters{0, 0, 0, 0, 0, 0, 0, 0};
 	const float ux = (float) (sc.cell_w[0] / 65535.), uy = (float) (sc.cell_w[1] / 65535.), uz = (float) (sc.cell_w[2] / 65535.); // shadow units
-	if(tid < 27) {
-		s_off[tid][0] = (float) ((double) (tid / 9 - 1) * sc.cell_w[0] - 8388608. * (double) ux);
-		s_off[tid][1] = (float) ((double) ((tid / 3) % 3 - 1) * sc.cell_w[1] - 8388608. * (double) uy);
-		s_off[tid][2] = (float) ((double) (tid % 3 - 1) * sc.cell_w[2] - 8388608. * (double) uz);
+	if(tid < 28) {
+		const double far = tid == kFarCode ? 1e4 : 0.;
+		s_off[tid] = make_float4((float) ((double) (tid / 9 - 1) * sc.cell_w[0] - 8388608. * (double) ux + far),
+				(float) ((double) ((tid / 3) % 3 - 1) * sc.cell_w[1] - 8388608. * (double) uy),
+				(float) ((double) (tid % 3 - 1) * sc.cell_w[2] - 8388608. * (double) uz), 0.f);
 	}
 	__syncthreads();
 
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
 	const float thr = (float) sc.sqr_rcut + kScreenBand;
 	const float core_lo = 1.f - kScreenBand, core_hi = 1.f + kScreenBand; // certain overlap below, certain clearance above
-	// (M^T d . b_i)^2 > cosmax^2 d^2 / base_z^2 with a 1e-3 relative band; -1 disables the screen (every pair in range goes to FP64)
+	// (M^T d . b_i)^2 > cosmax^2 d^2 / base_z^2 with a relative band; -1 disables the screen (every pair in range goes to FP64)
 	const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - kScreenBand) : -1.f;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -96,24 +106,23 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			prefetch_l2(ori + 9ll * (first + t) + 8);
 		}
 
-		// ---- stage the 27-cell neighbourhood: all copies in flight, one wait ------------------------------
+		// ---- stage the 27-cell neighbourhood, one column of three cells at a time: all copies in flight, one wait ----
 		int total = 0, self_base = 0;
-#pragma unroll 3
+		const int z0 = wrap_cell(iz - 1, nz), z2 = wrap_cell(iz + 1, nz);
+#pragma unroll 1
 		for(int c = 0; c < 9; c++) {
 			int cx = ix + c / 3 - 1;
 			if(!sc.slab) cx = wrap_cell(cx, sc.nxl); // (slab: an owned layer always has both x neighbours in the held range)
-			const int col = (cx * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
-#pragma unroll
-			for(int dz = -1; dz <= 1; dz++) {
-				const int zc = wrap_cell(iz + dz, nz);
-				const int b = cell_start[col + zc], e = cell_start[col + zc + 1];
-				if(c == 4 && dz == 0) self_base = total;
-				for(int s = b; s < e; s++, total++)
-					if(total < kNbCap) {
-						__pipeline_memcpy_async(&s_stage[total][tid], posf + s, 8);
-						s_tag[total][tid] = (unsigned char) (c * 3 + dz + 1);
-					}
-			}
+			const int *cs = cell_start + (cx * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
+			const int b0 = cs[z0], n0 = cs[z0 + 1] - b0, b1 = cs[iz], n01 = n0 + cs[iz + 1] - b1, b2 = cs[z2], n_col = n01 + cs[z2 + 1] - b2;
+			if(c == 4) self_base = total + n0;
+			for(int k = 0; k < n_col; k++, total++)
+				if(total < kNbCap) {
+					const int seg = (k >= n0) + (k >= n01);
+					const int s = k + (seg == 0 ? b0 : (seg == 1 ? b1 - n0 : b2 - n01));
+					__pipeline_memcpy_async(&s_stage[total][tid], posf + s, 8);
+					s_tag[total][tid] = (unsigned char) (c * 3 + seg);
+				}
 		}
 		__pipeline_commit();
 		const bool staged = total <= kNbCap;
@@ -130,9 +139,6 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			}
 			const double dx = pr->dx, dy = pr->dy, dz = pr->dz;
 			const double4 p4 = pos[sp];
-			double m[9]; // requested now, needed after the pre-screen: the latency hides behind it
-#pragma unroll
-			for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
 			const Vec3 p_old = {p4.x, p4.y, p4.z};
 			const Vec3 p_new = {__dadd_rn(p4.x, dx), __dadd_rn(p4.y, dy), __dadd_rn(p4.z, dz)};
 			int cx, cy, cz;
@@ -143,41 +149,28 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			const unsigned long long Wfix = (unsigned long long) pr->wfix;
 			tl.wt += Wfix;
 			const int j_self = self_base + pick;
-			const uint2 own = s_stage[j_self][tid];
-			const float fox = fmaf(shadow_lo(own.x), ux, s_off[13][0]), foy = fmaf(shadow_hi(own.x), uy, s_off[13][1]),
-					foz = fmaf(shadow_lo(own.y), uz, s_off[13][2]);
+			float fox, foy, foz;
+			shadow_position(s_stage[j_self][tid], s_off[13], ux, uy, uz, fox, foy, foz);
 			const float fnx = fox + (float) dx, fny = foy + (float) dy, fnz = foz + (float) dz;
 
 			// ---- 1. FP32 distance screen over the staged neighbourhood ---------------------
+			s_tag[j_self][tid] = (unsigned char) kFarCode; // the moved particle itself: out of everybody's range
 			int n_cand = 0;
 			bool ovl = false;
-#pragma unroll 2
 			for(int j = 0; j < total; j++) {
-				if(j == j_self) continue;
-				const uint2 q = s_stage[j][tid];
-				const unsigned code = s_tag[j][tid];
-				const float qx = fmaf(shadow_lo(q.x), ux, s_off[code][0]), qy = fmaf(shadow_hi(q.x), uy, s_off[code][1]),
-						qz = fmaf(shadow_lo(q.y), uz, s_off[code][2]);
+				float qx, qy, qz;
+				shadow_position(s_stage[j][tid], s_off[s_tag[j][tid]], ux, uy, uz, qx, qy, qz);
 				const float ax = qx - fox, ay = qy - foy, az = qz - foz;
 				const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
 				const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
 				const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
 				ovl |= d2n < core_lo;
-				const unsigned flags = (d2o < thr ? kNearOld : 0u) | (d2n < thr ? kNearNew : 0u);
-				if(flags) {
-					if(n_cand < kCandCap) s_cand[n_cand][tid] = (unsigned char) ((unsigned) j | flags);
-					n_cand++;
-				}
+				if(fminf(d2o, d2n) < thr) s_cand[n_cand++][tid] = (unsigned char) j; // n_cand < total <= kCandCap
 			}
+			s_tag[j_self][tid] = 13;
 			tl.checks += 2ull * (unsigned long long) (total - 1);
 			if(ovl) { // overlapping beyond any FP32 doubt: rejected whatever the bonds (MC.c:296-299, 332)
 				tl.ovl++;
-				continue;
-			}
-			if(n_cand > kCandCap) { // cannot happen for hard spheres with r_cut < 1.5; kept for safety
-				tl.wt -= Wfix;
-				tl.checks -= 2ull * (unsigned long long) (total - 1);
-				trial_serial(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
 				continue;
 			}
 
@@ -185,9 +178,11 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			// A bond needs one of the moved particle's patches to point at the neighbour (MC.c:249-255).
 			// With cosmax = 0.98 that is true for ~4 % of the pairs in the shell; the others are dismissed
 			// here from the FP32 separation and the FP32 copy of the particle's own matrix, through a
-			// relative band of 1e-3 on the squared cosine (the FP32 error is < 1e-5).  What survives --
-			// pointing or doubtful patches, separations within the band of the hard core -- goes to FP64.
-			double mn[9];
+			// relative band on the squared cosine.  What survives -- pointing or doubtful patches,
+			// separations within the band of the hard core -- goes to FP64.
+			double m[9], mn[9];
+#pragma unroll
+			for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
 #pragma unroll
 			for(int i = 0; i < 3; i++)
 #pragma unroll
@@ -201,23 +196,17 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 					mnf[k] = (float) mn[k];
 				}
 				for(int c0 = 0; c0 < n_cand; c0++) {
-					const unsigned e = s_cand[c0][tid];
-					const uint2 q = s_stage[e & kIdxMask][tid];
-					const unsigned code = s_tag[e & kIdxMask][tid];
-					const float qx = fmaf(shadow_lo(q.x), ux, s_off[code][0]), qy = fmaf(shadow_hi(q.x), uy, s_off[code][1]),
-							qz = fmaf(shadow_lo(q.y), uz, s_off[code][2]);
+					const unsigned j = s_cand[c0][tid];
+					float qx, qy, qz;
+					shadow_position(s_stage[j][tid], s_off[s_tag[j][tid]], ux, uy, uz, qx, qy, qz);
+					const float ax = qx - fox, ay = qy - foy, az = qz - foz;
+					const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
+					const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
+					const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
 					unsigned keep = 0u;
-					if(e & kNearNew) {
-						const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
-						const float d2 = fmaf(bz, bz, fmaf(by, by, bx * bx));
-						if(d2 < core_hi || may_point(mnf, bx, by, bz, d2, point_thr)) keep |= kNearNew;
-					}
-					if(e & kNearOld) {
-						const float ax = qx - fox, ay = qy - foy, az = qz - foz;
-						const float d2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
-						if(may_point(mf, ax, ay, az, d2, point_thr)) keep |= kNearOld;
-					}
-					if(keep) s_cand[n_exact++][tid] = (unsigned char) ((e & kIdxMask) | keep); // in place: n_exact <= c0
+					if(d2n < thr && (d2n < core_hi || may_point(mnf, bx, by, bz, d2n, point_thr))) keep |= kNearNew;
+					if(d2o < thr && may_point(mf, ax, ay, az, d2o, point_thr)) keep |= kNearOld;
+					if(keep) s_cand[n_exact++][tid] = (unsigned char) (j | keep); // in place: n_exact <= c0
 				}
 			}
 
@@ -249,7 +238,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				continue;
 			}
 
-			// ---- 3. Metropolis (MC.c:332-339) ------------------------------------------------
+			// ---- 4. Metropolis (MC.c:332-339) ------------------------------------------------
 			const int dE = b_old - b_new; // energy = -bonds
 			if(dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
 				double *p = reinterpret_cast<double *>(pos + sp); // x, y, z; the id in .w stays
