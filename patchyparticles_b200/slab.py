@@ -24,6 +24,7 @@ from .engine import Engine
 
 RECORD_DOUBLES = 13
 _DEBUG = bool(os.environ.get("PP_SLAB_DEBUG"))
+PARANOID = bool(os.environ.get("PP_SLAB_PARANOID"))  # check the halo populations after every rebuild
 
 
 def _dbg(rank, *a):
@@ -107,6 +108,8 @@ class SlabEngine:
         self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.eng.slab_setup(rank, world)
         self.N = 0
+        self._halo_cache = [None, None]
+        self._rebuilds = 0
 
     def close(self):
         self.eng.close()
@@ -114,6 +117,7 @@ class SlabEngine:
     def upload(self, box, r, orient):
         self.N = int(np.asarray(r).reshape(-1, 3).shape[0])
         self.eng.upload(box, r, orient)  # every rank sees the whole configuration and keeps its layers
+        self._halo_cache = [None, None]
 
     def _allreduce(self, values, op=dist.ReduceOp.SUM):
         t = torch.tensor(values, dtype=torch.int64, device=self.device)
@@ -139,16 +143,22 @@ class SlabEngine:
         b, ov, running, bad = self._allreduce([b, ov, running, 0 if ok_local else 1])
         return b, int(ov > 0), (b == running and ov == 0 and bad == 0)
 
-    def _halo_refresh(self, send_side):
-        """send_side 0: first owned layer -> left neighbour (its right halo); 1: last owned layer -> right."""
+    def _halo_views(self, send_side):
+        """Zero-copy views of the layer slices of one halo refresh; they only change when the cells are rebuilt."""
         e, dev = self.eng, self.device
         sp, so, sf, ns = e.slab_halo(send_side, recv=False)
         rp, ro, rf, nr = e.slab_halo(1 - send_side, recv=True)
-        _dbg(self.rank, "halo refresh side", send_side, "send", ns, "recv", nr)
         send = [device_view(sp, 4 * ns, torch.float64, dev), device_view(so, 9 * ns, torch.float64, dev),
                 device_view(sf, 2 * ns, torch.int32, dev)]
         recv = [device_view(rp, 4 * nr, torch.float64, dev), device_view(ro, 9 * nr, torch.float64, dev),
                 device_view(rf, 2 * nr, torch.int32, dev)]
+        return send, recv
+
+    def _halo_refresh(self, send_side):
+        """send_side 0: first owned layer -> left neighbour (its right halo); 1: last owned layer -> right."""
+        if self._halo_cache[send_side] is None:
+            self._halo_cache[send_side] = self._halo_views(send_side)
+        send, recv = self._halo_cache[send_side]
         if send_side == 0:
             exchange_with_neighbours(self.rank, self.world, send, [], [], recv)
         else:
@@ -181,7 +191,10 @@ class SlabEngine:
                     [device_view(il, RECORD_DOUBLES * n_from_l, torch.float64, dev)], [device_view(ir, RECORD_DOUBLES * n_from_r, torch.float64, dev)])
                 e.slab_sweep_rebuild()
                 _dbg(self.rank, "rebuilt", e.slab_range())
-                self._check_halo_counts()
+                self._halo_cache = [None, None]
+                self._rebuilds += 1
+                if self._rebuilds <= 4 or self._rebuilds % 16 == 0 or PARANOID:  # the check costs a host synchronisation
+                    self._check_halo_counts()
             e.slab_pass_block(0)
             self._halo_refresh(0)
             e.slab_pass_block(1)
