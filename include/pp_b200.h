@@ -159,7 +159,7 @@ int pp_reset_kernel_stats(pp_handle *h);
  *     pp_slab_pass_block(1);  last owned layer  -> right neighbour's left halo
  *     pp_slab_sweep_end()
  * Records are 13 doubles (x, y, z, id, orientation[9]); halo views are contiguous slices of the
- * engine's position (double4), orientation (9 doubles) and FP32 shadow (float4) arrays.  All
+ * engine's position (double4), orientation (9 doubles) and fixed-point shadow (uint2) arrays.  All
  * pointers returned here are DEVICE pointers.  NVT only. */
 int pp_slab_setup(pp_handle *h, int rank, int world);
 int pp_slab_range(pp_handle *h, int *x0, int *x1, int *nx, int *n_local);
@@ -169,6 +169,17 @@ int pp_slab_inbox(pp_handle *h, int side, int count, void **dev);
 int pp_slab_sweep_rebuild(pp_handle *h);
 int pp_slab_pass_block(pp_handle *h, int cx);
 int pp_slab_halo(pp_handle *h, int side, int recv, void **pos, void **ori, void **posf, int *count);
+ /* Halo refresh over peer memory, for engines on the GPUs of one NVLink / NVSwitch node (replaces the
+ * library transfers of the pp_slab_halo slices).  Every engine exports a mailbox block as a 64-byte
+ * cudaIpcMemHandle_t after pp_upload, the driver hands each engine the handles of its left and right
+ * neighbour, and pp_slab_refresh(side) then (1) stores the engine's first (side 0) / last (side 1) owned
+ * layer into the neighbour's mailbox and publishes a sequence number there, (2) waits on the device for the
+ * matching number in its own mailbox and moves it into its right (side 0) / left (side 1) halo layer.  Nothing
+ * synchronises with the host; a neighbour that never shows up is reported by pp_sync after 20 s. */
+int pp_slab_peer_export(pp_handle *h, void *ipc_handle_64);
+int pp_slab_peer_connect(pp_handle *h, const void *left_handle_64, const void *right_handle_64);
+int pp_slab_refresh(pp_handle *h, int side);
+int pp_slab_peer_close(pp_handle *h);
 int pp_slab_sweep_end(pp_handle *h);
 int pp_slab_download(pp_handle *h, int *n_owned, int *ids, double *r, double *orient);
 

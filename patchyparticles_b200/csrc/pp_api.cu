@@ -100,6 +100,17 @@ struct pp_handle {
 	bool slab_pending;   // a classify has been done and waits for pp_slab_sweep_rebuild
 	int layer_slots[6];  // slot offsets: left halo begin, first owned begin, first owned end, last owned begin, right halo begin, right halo end
 
+	// peer-memory halo refresh: my mailbox block ([from-left mailbox][from-right mailbox][2 flags]) and the
+	// neighbours' blocks mapped with CUDA IPC
+	char *mbox;
+	size_t mbox_stride;           // bytes per mailbox
+	long long mbox_cap;           // particles per mailbox
+	char *peer_mbox[2];           // left / right neighbour's block
+	bool peer_same, peer_connected;
+	unsigned long long halo_epoch[2];
+	unsigned int *d_push_done;
+	int *d_peer_status;
+
 	// the two sweep kernels of a colour pass run concurrently: crowded cells (tile kernel) on `stream`, sparsely
 	// populated ones (thread-per-cell kernel) on `stream2`
 	cudaStream_t stream2;
@@ -128,6 +139,21 @@ int fail(pp_handle *h, const char *fmt, ...) {
 		cudaError_t e_ = (call);                                                                              \
 		if(e_ != cudaSuccess) return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
 	} while(0)
+
+void peer_release(pp_handle *h) {
+	if(h->peer_connected) {
+		cudaIpcCloseMemHandle(h->peer_mbox[0]);
+		if(!h->peer_same) cudaIpcCloseMemHandle(h->peer_mbox[1]);
+	}
+	h->peer_connected = false;
+	h->peer_mbox[0] = h->peer_mbox[1] = nullptr;
+	cudaFree(h->mbox);
+	cudaFree(h->d_push_done);
+	cudaFree(h->d_peer_status);
+	h->mbox = nullptr;
+	h->d_push_done = nullptr;
+	h->d_peer_status = nullptr;
+}
 
 void base_patches_host(double *base) {
 	// system.c:20-31
@@ -641,6 +667,7 @@ int pp_destroy(pp_handle *h) {
 		cudaFree(h->inbox[k]);
 	}
 	cudaFree(h->d_slab_counts);
+	peer_release(h);
 	cudaFreeHost(h->h_counters);
 	if(h->ev0) cudaEventDestroy(h->ev0);
 	if(h->ev1) cudaEventDestroy(h->ev1);
@@ -827,6 +854,11 @@ int pp_sweep(pp_handle *h, long long nsteps) {
 int pp_sync(pp_handle *h) {
 	if(h == nullptr) return 1;
 	CUDA_OK(h, cudaStreamSynchronize(h->stream));
+	if(h->peer_connected) {
+		int status = 0;
+		CUDA_OK(h, cudaMemcpy(&status, h->d_peer_status, sizeof(int), cudaMemcpyDeviceToHost));
+		if(status) return fail(h, "a halo refresh timed out waiting for the neighbouring engine");
+	}
 	return 0;
 }
 
@@ -1111,6 +1143,79 @@ int pp_slab_halo(pp_handle *h, int side, int recv, void **pos, void **ori, void 
 	if(ori) *ori = h->ori[h->co] + 9ll * b;
 	if(posf) *posf = h->cb.posf + b;
 	if(count) *count = e - b;
+	return 0;
+}
+
+// ---- halo refresh over peer memory -------------------------------------------------------------------
+int pp_slab_peer_export(pp_handle *h, void *ipc_handle_64) {
+	if(h == nullptr || ipc_handle_64 == nullptr) return 1;
+	if(h->slab_world <= 1 || !h->cells_valid) return fail(h, "pp_slab_peer_export: upload a configuration in slab mode first");
+	CUDA_OK(h, cudaSetDevice(h->device));
+	CUDA_OK(h, cudaStreamSynchronize(h->stream));
+	peer_release(h);
+	h->mbox_cap = h->cap_records;
+	h->mbox_stride = ((size_t) h->mbox_cap * 112 + 255) / 256 * 256;
+	const size_t bytes = 2 * h->mbox_stride + 256;
+	CUDA_OK(h, cudaMalloc(&h->mbox, bytes));
+	CUDA_OK(h, cudaMemset(h->mbox, 0, bytes));
+	CUDA_OK(h, cudaMalloc(&h->d_push_done, sizeof(unsigned int)));
+	CUDA_OK(h, cudaMemset(h->d_push_done, 0, sizeof(unsigned int)));
+	CUDA_OK(h, cudaMalloc(&h->d_peer_status, sizeof(int)));
+	CUDA_OK(h, cudaMemset(h->d_peer_status, 0, sizeof(int)));
+	h->halo_epoch[0] = h->halo_epoch[1] = 0;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 bytes");
+	cudaIpcMemHandle_t mh;
+	CUDA_OK(h, cudaIpcGetMemHandle(&mh, h->mbox));
+	memcpy(ipc_handle_64, &mh, 64);
+	return 0;
+}
+
+int pp_slab_peer_connect(pp_handle *h, const void *left_handle_64, const void *right_handle_64) {
+	if(h == nullptr || left_handle_64 == nullptr || right_handle_64 == nullptr) return 1;
+	if(h->mbox == nullptr) return fail(h, "pp_slab_peer_connect before pp_slab_peer_export");
+	CUDA_OK(h, cudaSetDevice(h->device));
+	cudaIpcMemHandle_t l, r;
+	memcpy(&l, left_handle_64, 64);
+	memcpy(&r, right_handle_64, 64);
+	h->peer_same = memcmp(&l, &r, 64) == 0; // two engines: both neighbours are the same one
+	CUDA_OK(h, cudaIpcOpenMemHandle((void **) &h->peer_mbox[0], l, cudaIpcMemLazyEnablePeerAccess));
+	if(h->peer_same) h->peer_mbox[1] = h->peer_mbox[0];
+	else CUDA_OK(h, cudaIpcOpenMemHandle((void **) &h->peer_mbox[1], r, cudaIpcMemLazyEnablePeerAccess));
+	h->peer_connected = true;
+	return 0;
+}
+
+int pp_slab_peer_close(pp_handle *h) {
+	if(h == nullptr) return 1;
+	if(h->stream) cudaStreamSynchronize(h->stream);
+	peer_release(h);
+	return 0;
+}
+
+// side 0: my first owned layer -> the left neighbour's right halo, then my right halo <- what the right neighbour
+// pushed; side 1: my last owned layer -> the right neighbour's left halo, then my left halo <- the left neighbour.
+int pp_slab_refresh(pp_handle *h, int side) {
+	if(h == nullptr || side < 0 || side > 1) return 1;
+	if(!h->peer_connected || !h->cells_valid) return fail(h, "pp_slab_refresh: no peer connection / no valid slab layout");
+	CUDA_OK(h, cudaSetDevice(h->device));
+	const int sb = side == 0 ? h->layer_slots[1] : h->layer_slots[3], se = side == 0 ? h->layer_slots[2] : h->layer_slots[4];
+	const int rb = side == 0 ? h->layer_slots[4] : h->layer_slots[0], re = side == 0 ? h->layer_slots[5] : h->layer_slots[1];
+	if(se - sb > h->mbox_cap || re - rb > h->mbox_cap) return fail(h, "halo layer of %d particles exceeds the mailbox capacity %lld", se - sb > re - rb ? se - sb : re - rb, h->mbox_cap);
+	const unsigned long long epoch = ++h->halo_epoch[side];
+	// the neighbour's mailbox for data coming from me: its from-right box (1) when I am its right neighbour (side 0)
+	const int box = side == 0 ? 1 : 0;
+	char *peer = h->peer_mbox[side == 0 ? 0 : 1];
+	unsigned long long *peer_flags = reinterpret_cast<unsigned long long *>(peer + 2 * h->mbox_stride);
+	const unsigned long long *my_flags = reinterpret_cast<const unsigned long long *>(h->mbox + 2 * h->mbox_stride);
+	double4 *pos = h->pos[h->cp];
+	double *ori = h->ori[h->co];
+	prof_begin(h);
+	int nl = launch_halo_push(pos + sb, ori + 9ll * sb, h->cb.posf + sb, se - sb, peer + box * h->mbox_stride, h->mbox_cap, peer_flags + box, epoch,
+			h->d_push_done, h->stream);
+	nl += launch_halo_pull(h->mbox + box * h->mbox_stride, h->mbox_cap, my_flags + box, epoch, pos + rb, ori + 9ll * rb, h->cb.posf + rb, re - rb,
+			h->d_peer_status, h->stream);
+	prof_end(h, PP_K_CELLS, nl);
+	CUDA_OK(h, cudaGetLastError());
 	return 0;
 }
 

@@ -89,6 +89,10 @@ int launch_slab_classify(const SimConst &sc_new, int slot_begin, int slot_end, i
 		double *out_left, double *out_right, int cap_records, int *counts, cudaStream_t st);
 int launch_slab_unpack(int n, const double *records, int offset, const StateView &dst, cudaStream_t st);
 int launch_slab_download(int slot_begin, int slot_end, const StateView &cur, int *ids, double *r, double *orient, cudaStream_t st);
+int launch_halo_push(const double4 *pos, const double *ori, const uint2 *posf, int n, char *peer_mbox, long long cap, unsigned long long *peer_flag,
+		unsigned long long epoch, unsigned int *done, cudaStream_t st);
+int launch_halo_pull(const char *mbox, long long cap, const unsigned long long *flag, unsigned long long epoch, double4 *pos, double *ori, uint2 *posf,
+		int n, int *status, cudaStream_t st);
 
 // upload / download helpers (caller order <-> slot order)
 int launch_pack_state(int N, const double *r, const double *orient, double4 *pos, double *ori, int *pid, cudaStream_t st);

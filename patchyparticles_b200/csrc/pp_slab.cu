@@ -12,6 +12,14 @@
 //   k_slab_unpack    appends the records received from a neighbour to the kept particles;
 //   k_slab_download  compacts the owned particles for output.
 // A record is 13 doubles: x, y, z, id, orientation[9].
+//
+// In-period halo refresh over peer memory (all engines on one NVLink / NVSwitch node): every engine
+// owns two mailboxes that its neighbours map with CUDA IPC.
+//   k_halo_push  copies a boundary layer (positions, orientations, shadows) straight into the
+//                neighbour's mailbox with NVLink stores; the last block to finish publishes the
+//                refresh number in the neighbour's flag (release, system scope);
+//   k_halo_pull  waits for that flag (acquire, system scope) and moves the mailbox into the halo
+//                layer.  No host synchronisation, no collective library call on the sweep path.
 #include "pp_kernels.cuh"
 
 namespace pp {
@@ -95,6 +103,73 @@ __global__ void __launch_bounds__(256) k_slab_download(int slot_begin, int slot_
 	r[3ll * i + 2] = p.z;
 #pragma unroll
 	for(int k = 0; k < 9; k++) orient[9ll * i + k] = ori[9ll * s + k];
+}
+
+__global__ void __launch_bounds__(256) k_halo_push(const double4 *__restrict__ pos, const double *__restrict__ ori, const uint2 *__restrict__ posf, int n,
+		char *mbox /* peer memory */, long long cap, unsigned long long *flag /* peer memory */, unsigned long long epoch, unsigned int *done) {
+	double2 *mp = reinterpret_cast<double2 *>(mbox);
+	double *mo = reinterpret_cast<double *>(mbox + 32ll * cap);
+	uint2 *mf = reinterpret_cast<uint2 *>(mbox + 104ll * cap);
+	const double2 *p2 = reinterpret_cast<const double2 *>(pos);
+	const long long stride = (long long) gridDim.x * blockDim.x, i0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	for(long long i = i0; i < 2ll * n; i += stride) mp[i] = p2[i];
+	for(long long i = i0; i < n; i += stride) mf[i] = posf[i];
+	for(long long i = i0; i < 9ll * n; i += stride) mo[i] = ori[i];
+	__threadfence_system();
+	__syncthreads();
+	if(threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) { // every block's stores are out: publish
+		*done = 0;
+		__threadfence_system();
+		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+	}
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+__global__ void __launch_bounds__(256) k_halo_pull(const char *__restrict__ mbox, long long cap, const unsigned long long *flag, unsigned long long epoch,
+		double4 *__restrict__ pos, double *__restrict__ ori, uint2 *__restrict__ posf, int n, int *status) {
+	if(threadIdx.x == 0) {
+		const unsigned long long t0 = global_timer_ns();
+		for(;;) {
+			unsigned long long v;
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+			if(v >= epoch) break;
+			if(global_timer_ns() - t0 > 20000000000ull) { // 20 s: the neighbour is gone; report instead of hanging
+				atomicExch(status, 1);
+				break;
+			}
+			__nanosleep(200);
+		}
+	}
+	__syncthreads();
+	const double2 *mp = reinterpret_cast<const double2 *>(mbox);
+	const double *mo = reinterpret_cast<const double *>(mbox + 32ll * cap);
+	const uint2 *mf = reinterpret_cast<const uint2 *>(mbox + 104ll * cap);
+	double2 *p2 = reinterpret_cast<double2 *>(pos);
+	const long long stride = (long long) gridDim.x * blockDim.x, i0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	for(long long i = i0; i < 2ll * n; i += stride) p2[i] = __ldcg(mp + i);
+	for(long long i = i0; i < n; i += stride) posf[i] = __ldcg(mf + i);
+	for(long long i = i0; i < 9ll * n; i += stride) ori[i] = __ldcg(mo + i);
+}
+
+int launch_halo_push(const double4 *pos, const double *ori, const uint2 *posf, int n, char *peer_mbox, long long cap, unsigned long long *peer_flag,
+		unsigned long long epoch, unsigned int *done, cudaStream_t st) {
+	int blocks = (9 * n + 255) / 256;
+	blocks = blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks);
+	k_halo_push<<<blocks, 256, 0, st>>>(pos, ori, posf, n, peer_mbox, cap, peer_flag, epoch, done);
+	return 1;
+}
+
+int launch_halo_pull(const char *mbox, long long cap, const unsigned long long *flag, unsigned long long epoch, double4 *pos, double *ori, uint2 *posf,
+		int n, int *status, cudaStream_t st) {
+	int blocks = (9 * n + 255) / 256;
+	blocks = blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks);
+	k_halo_pull<<<blocks, 256, 0, st>>>(mbox, cap, flag, epoch, pos, ori, posf, n, status);
+	return 1;
 }
 
 int launch_slab_classify(const SimConst &sc_new, int slot_begin, int slot_end, int x0, int n_owned_layers, const StateView &cur, const StateView &keep,

@@ -54,7 +54,8 @@ ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy",
                "pp_check_energy", "pp_eval_proposals", "pp_volume_move", "pp_Lx_move", "pp_set_stream",
                "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats", "pp_slab_setup", "pp_slab_range",
                "pp_slab_sweep_begin", "pp_slab_outbox", "pp_slab_inbox", "pp_slab_sweep_rebuild", "pp_slab_pass_block",
-               "pp_slab_halo", "pp_slab_sweep_end", "pp_slab_download"]
+               "pp_slab_halo", "pp_slab_sweep_end", "pp_slab_download", "pp_slab_peer_export", "pp_slab_peer_connect",
+               "pp_slab_refresh", "pp_slab_peer_close"]
 
 
 def load_library():
@@ -99,6 +100,10 @@ def load_library():
     L.pp_slab_pass_block.argtypes = [H, C.c_int]
     L.pp_slab_halo.argtypes = [H, C.c_int, C.c_int, PV, PV, PV, PI]
     L.pp_slab_sweep_end.argtypes = [H]
+    L.pp_slab_peer_export.argtypes = [H, C.c_char_p]
+    L.pp_slab_peer_connect.argtypes = [H, C.c_char_p, C.c_char_p]
+    L.pp_slab_refresh.argtypes = [H, C.c_int]
+    L.pp_slab_peer_close.argtypes = [H]
     L.pp_slab_download.argtypes = [H, PI, _ip, _dp, _dp]
     _lib = L
     return L
@@ -256,6 +261,21 @@ class Engine:
 
     def slab_sweep_end(self):
         self._check(self.L.pp_slab_sweep_end(self.h))
+
+    def slab_peer_export(self):
+        """-> the 64-byte CUDA IPC handle of this engine's halo mailboxes"""
+        buf = C.create_string_buffer(64)
+        self._check(self.L.pp_slab_peer_export(self.h, buf))
+        return buf.raw
+
+    def slab_peer_connect(self, left_handle, right_handle):
+        self._check(self.L.pp_slab_peer_connect(self.h, left_handle, right_handle))
+
+    def slab_refresh(self, side):
+        self._check(self.L.pp_slab_refresh(self.h, int(side)))
+
+    def slab_peer_close(self):
+        self._check(self.L.pp_slab_peer_close(self.h))
 
     def slab_download(self):
         n = C.c_int(0)

@@ -25,6 +25,7 @@ from .engine import Engine
 RECORD_DOUBLES = 13
 _DEBUG = bool(os.environ.get("PP_SLAB_DEBUG"))
 PARANOID = bool(os.environ.get("PP_SLAB_PARANOID"))  # check the halo populations after every rebuild
+HALO_TRANSPORT = os.environ.get("PP_SLAB_HALO", "peer")  # "peer": stores into the neighbour's memory over NVLink; "nccl": send/recv
 
 
 def _dbg(rank, *a):
@@ -110,14 +111,32 @@ class SlabEngine:
         self.N = 0
         self._halo_cache = [None, None]
         self._rebuilds = 0
+        self.peer_halo = HALO_TRANSPORT == "peer"
 
     def close(self):
+        if self.peer_halo:
+            self.eng.sync()
+            dist.barrier()  # nobody unmaps while a neighbour may still push
+            self.eng.slab_peer_close()
+            dist.barrier()
         self.eng.close()
 
     def upload(self, box, r, orient):
         self.N = int(np.asarray(r).reshape(-1, 3).shape[0])
         self.eng.upload(box, r, orient)  # every rank sees the whole configuration and keeps its layers
         self._halo_cache = [None, None]
+        self._rebuilds = 0
+        if self.peer_halo:
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """Every engine exports its halo mailboxes (CUDA IPC) and maps those of its ring neighbours."""
+        mine = self.eng.slab_peer_export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine)
+        left, right = neighbours(self.rank, self.world)
+        self.eng.slab_peer_connect(handles[left], handles[right])
+        dist.barrier()  # nobody pushes before everybody has mapped
 
     def _allreduce(self, values, op=dist.ReduceOp.SUM):
         t = torch.tensor(values, dtype=torch.int64, device=self.device)
@@ -156,6 +175,9 @@ class SlabEngine:
 
     def _halo_refresh(self, send_side):
         """send_side 0: first owned layer -> left neighbour (its right halo); 1: last owned layer -> right."""
+        if self.peer_halo:
+            self.eng.slab_refresh(send_side)
+            return
         if self._halo_cache[send_side] is None:
             self._halo_cache[send_side] = self._halo_views(send_side)
         send, recv = self._halo_cache[send_side]
