@@ -34,6 +34,7 @@ WORKLOADS = {
     "64k": (65536, 0.5, 0.1),
     "1k": (1000, 0.1, 0.1),
     "256k": (262144, 0.5, 0.1),
+    "512k": (524288, 0.6, 0.1),
     "1M": (1048576, 0.6, 0.1),
     "4M": (4194304, 0.6, 0.1),
 }
@@ -233,7 +234,7 @@ class Arm:
         import torch
         N, rho, T = WORKLOADS[w]
         params = dict(temperature=T, kf_delta=KF_DELTA, kf_cosmax=KF_COSMAX, disp_max=DISP_MAX, theta_max=THETA_MAX,
-                      lanes_per_cell=args.lanes)
+                      lanes_per_cell=args.lanes, cells_max_occupancy=args.cells_max_occupancy, cell_lanes=args.cell_lanes)
         self.sharded = sharded
         if sharded:
             from patchyparticles_b200.slab import SlabEngine
@@ -279,7 +280,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas of the 1-GPU workload instead of one sharded system")
-    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0, help="tile width of the tile kernel (0: auto, 1: thread-per-cell kernel wherever it fits)")
+    ap.add_argument("--cell-lanes", type=int, default=0, help="lanes per cell of the thread-per-cell kernel (0: auto, 1, 2, 4, 8)")
+    ap.add_argument("--cells-max-occupancy", type=int, default=-1,
+                    help="cells with at most this many particles go to the thread-per-cell kernel (-1: auto, 0: tile kernel only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--relax-sweeps", type=int, default=300,

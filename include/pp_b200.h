@@ -60,7 +60,7 @@ typedef struct pp_params {
 	int device;                 /* CUDA device ordinal */
 	int lanes_per_cell;         /* 0 = default (hybrid: sparse cells one thread each, crowded cells one tile each);
 	                               1 = every cell one thread; 4, 8, 16, 32 = every cell one tile of that width */
-	int use_graph;              /* 1: replay the per-sweep launch sequence as a CUDA graph */
+	int cell_lanes;             /* lanes per cell of the thread-per-cell sweep kernel: 0 auto, 1, 2, 4, 8 */
 	int cells_max_occupancy;    /* hybrid mode: cells with at most this many particles go to the thread-per-cell kernel; -1 = default (3) */
 	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
 } pp_params;
@@ -180,6 +180,8 @@ int pp_slab_peer_export(pp_handle *h, void *ipc_handle_64);
 int pp_slab_peer_connect(pp_handle *h, const void *left_handle_64, const void *right_handle_64);
 int pp_slab_refresh(pp_handle *h, int side);
 int pp_slab_peer_close(pp_handle *h);
+/* whole sweeps over peer memory until max_sweeps are done or the next grid shift needs pp_slab_sweep_begin */
+int pp_slab_sweeps(pp_handle *h, int max_sweeps, int *done);
 int pp_slab_sweep_end(pp_handle *h);
 int pp_slab_download(pp_handle *h, int *n_owned, int *ids, double *r, double *orient);
 

@@ -324,9 +324,19 @@ int cells_occupancy_limit(const pp_handle *h) {
 	const bool grid_ok = (h->slab_world > 1 || h->n_side[0] >= 4) && h->n_side[1] >= 4 && h->n_side[2] >= 4;
 	if(!grid_ok) return 0;
 	if(h->prm.lanes_per_cell == 1) return kWorkBuckets - 1;
-	if(h->prm.lanes_per_cell != 0) return 0;
 	if(h->prm.cells_max_occupancy >= 0) return h->prm.cells_max_occupancy < kWorkBuckets ? h->prm.cells_max_occupancy : kWorkBuckets - 1;
-	return (h->N >= 400000) ? 3 : 0; // small systems are bound by the serial chain of a cell: tiles only (profiles/README.md)
+	if(h->prm.lanes_per_cell != 0) return 0; // an explicit tile width alone: tile kernel only
+	// measured on B200 (profiles/README.md): the thread-per-cell kernel wins once a colour pass fills the GPU; the
+	// smaller the pass, the more its serial chain per cell matters and the fewer particles a cell may hold there
+	return (h->N >= 800000) ? 3 : ((h->N >= 300000) ? 2 : 0);
+}
+
+// lanes per cell of the thread-per-cell kernel: one lane per cell has the highest throughput, more lanes shorten
+// the serial chain of a cell when a colour pass is too small to fill the GPU
+int cell_lanes(const pp_handle *h) {
+	const int l = h->prm.cell_lanes;
+	if(l == 1 || l == 2 || l == 4 || l == 8) return l;
+	return 1;
 }
 
 int tile_lanes(const pp_handle *h) {
@@ -348,9 +358,13 @@ int launch_passes(pp_handle *h, const SimConst &sc, int first_pass, int n_pass) 
 	for(int pass = first_pass; pass < first_pass + n_pass; pass++) {
 		const int colour = ((pass >> 2) & 1) | (((pass >> 1) & 1) << 1) | ((pass & 1) << 2);
 		const int *ranges = h->cb.bins + kWorkRanges + 4 * colour;
-		nl += launch_sweep_pass(sc, ranges, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
+		// crowded cells: the tile kernel, or (hybrid routing, no explicit tile width) the 8-lane latency configuration
+		// of the thread-per-cell kernel
+		if(limit > 0 && h->prm.lanes_per_cell == 0)
+			nl += launch_sweep_cells(sc, ranges, n_active, 8, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
+		else nl += launch_sweep_pass(sc, ranges, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream);
 		if(limit > 0) {
-			nl += launch_sweep_cells(sc, ranges + 2, n_active, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream2);
+			nl += launch_sweep_cells(sc, ranges + 2, n_active, cell_lanes(h), h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->stream2);
 			// the next pass (either kernel) starts when both kernels of this one are done
 			cudaEventRecord(h->ev_a, h->stream);
 			cudaEventRecord(h->ev_b, h->stream2);
@@ -1216,6 +1230,25 @@ int pp_slab_refresh(pp_handle *h, int side) {
 			h->d_peer_status, h->stream);
 	prof_end(h, PP_K_CELLS, nl);
 	CUDA_OK(h, cudaGetLastError());
+	return 0;
+}
+
+// Runs whole sweeps (pass block, refresh, pass block, refresh) over peer memory until `max_sweeps` are done or the
+// next grid shift needs a migration exchange, which is the driver's job.  -> number of sweeps done in *done.
+int pp_slab_sweeps(pp_handle *h, int max_sweeps, int *done) {
+	if(h == nullptr || done == nullptr) return 1;
+	*done = 0;
+	if(!h->peer_connected) return fail(h, "pp_slab_sweeps needs the peer-memory halo refresh (pp_slab_peer_connect)");
+	const long long period = h->prm.shift_every;
+	while(*done < max_sweeps) {
+		if(!(h->sweep_grid && h->cells_valid && h->step % period != 0)) break; // a new shift period starts here
+		for(int cx = 0; cx < 2; cx++) {
+			if(pp_slab_pass_block(h, cx)) return 1;
+			if(pp_slab_refresh(h, cx)) return 1;
+		}
+		h->step++;
+		(*done)++;
+	}
 	return 0;
 }
 

@@ -65,7 +65,7 @@ int launch_proposals_for_sweep(const SimConst &sc, const CellBuffers &cb, Propos
 int launch_sweep_pass(const SimConst &sc, const int *range, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
 		Counters *counters, cudaStream_t st);
 // ... or one thread per cell (sparsely populated cells; needs at least 3 distinct cells per axis)
-int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
+int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
 		double *ori, Counters *counters, cudaStream_t st);
 
 // K3: full bond count + overlap flag into counters->bonds / counters->overlap (zeroed by the launcher)

@@ -67,15 +67,44 @@ __device__ __forceinline__ void shadow_position(const uint2 q, const float4 off,
 
 constexpr int kFarCode = 27; // tag of an entry that must not pair with anything: its cell offset is far outside the screens
 
+// staging capacity of one lane (neighbours per lane); a cell whose neighbourhood does not fit takes the serial path
+__host__ __device__ constexpr int lane_cap(int G) { return G == 1 ? kCellsNbCap : (G == 2 ? 32 : 24); }
+
+// Latency configuration (G >= 4): the proposals of the cell's trials and the FP64 state of its own particles are
+// staged too, so that a trial of a crowded cell does not wait for global memory between its steps.
+constexpr int kMaxOwn = 8;
+struct OwnStage {
+	Proposal pr[kMaxOwn];
+	double4 pos[kMaxOwn];
+	double ori[kMaxOwn * 9];
+};
+
+// G lanes per cell.  Lane l stages and screens the columns c = l, l + G, ... of the 3 x 3 columns of the
+// neighbourhood and runs the FP64 tests of its own candidates; the lanes meet three times per trial (overlap
+// flag after the distance screen, bond counts after the FP64 tests, via shuffles inside the group).  G = 1 is
+// the throughput configuration; G > 1 shortens the serial chain of a cell when a pass is too small to
+// fill the machine.
+template<int G>
 __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
 		uint2 *posf, Counters *__restrict__ counters) {
-	__shared__ __align__(8) uint2 s_stage[kNbCap][kCellThreads]; // [entry][thread]: shadow of a staged neighbour
-	__shared__ unsigned char s_tag[kNbCap][kCellThreads];       // its neighbour-cell code, 0 .. 26
-	__shared__ unsigned char s_cand[kCandCap][kCellThreads];
+	constexpr int kCap = lane_cap(G);
+	constexpr bool kOwn = G >= 4;
+	constexpr int kGroups = kCellThreads / G;
+	constexpr int kOwner = 4 % G; // the lane that stages the home column (c = 4) holds the moved particle's entry and does the book-keeping
+	__shared__ __align__(8) uint2 s_stage[kCap][kCellThreads]; // [entry][thread]: shadow of a staged neighbour
+	__shared__ unsigned char s_tag[kCap][kCellThreads];       // its neighbour-cell code, 0 .. 26
+	__shared__ unsigned char s_cand[kCap][kCellThreads];
 	__shared__ __align__(16) float4 s_off[28]; // offset of neighbour cell `code` from the home cell, minus 2^23 shadow units
 	__shared__ CellBlockCounters s_cnt;
+	__shared__ __align__(16) OwnStage s_own[kOwn ? kGroups : 1];
 	const int tid = threadIdx.x;
+	if((long long) blockIdx.x * kGroups >= range[1] - range[0]) return; // the grid is sized for the worst case: nothing left for this block
+	const int gl = tid & (G - 1); // lane inside the group
+	OwnStage &os = s_own[kOwn ? tid / G : 0];
+	const unsigned gmask = (G == 1) ? 0u : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
+	const int owner_lane = ((tid & 31) & ~(G - 1)) + kOwner; // warp lane of the group's owner
+	const bool is_owner = gl == kOwner;
 	if(tid == 0) s_cnt = CellBlockCounters{0, 0, 0, 0, 0, 0, 0, 0};
 	const float ux = (float) (sc.cell_w[0] / 65535.), uy = (float) (sc.cell_w[1] / 65535.), uz = (float) (sc.cell_w[2] / 65535.); // shadow units
 	if(tid < 28) {
@@ -94,67 +123,94 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 	const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - kScreenBand) : -1.f;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0, 0};
 
-	for(int wi = w_begin + blockIdx.x * kCellThreads + tid; wi < w_end; wi += gridDim.x * kCellThreads) {
+	for(int wi = w_begin + blockIdx.x * kGroups + tid / G; wi < w_end; wi += gridDim.x * kGroups) {
 		const int cell = work[wi];
 		const int ix = cell / nyz, iy = (cell - ix * nyz) / nz, iz = cell - ix * nyz - iy * nz;
 		const int first = cell_start[cell];
 		const int n_here = cell_start[cell + 1] - first;
-		for(int t = 0; t < n_here; t++) { // the cell's own trials: on their way to L2 while the neighbourhood is staged
-			prefetch_l2(proposals + first + t);
-			prefetch_l2(pos + first + t);
-			prefetch_l2(ori + 9ll * (first + t));
-			prefetch_l2(ori + 9ll * (first + t) + 8);
+		const bool own_staged = kOwn && n_here <= kMaxOwn;
+		if(own_staged) { // the cell's proposals and its particles' FP64 state: staged with the neighbourhood
+			__syncwarp(gmask); // the group is done with the previous cell
+			for(int i = gl; i < 7 * n_here; i += G)
+				__pipeline_memcpy_async(reinterpret_cast<char *>(os.pr) + 16 * i, reinterpret_cast<const char *>(proposals + first) + 16 * i, 16);
+			for(int i = gl; i < 2 * n_here; i += G)
+				__pipeline_memcpy_async(reinterpret_cast<char *>(os.pos) + 16 * i, reinterpret_cast<const char *>(pos + first) + 16 * i, 16);
+			for(int i = gl; i < 9 * n_here; i += G) __pipeline_memcpy_async(os.ori + i, ori + 9ll * first + i, 8);
 		}
+		else
+			for(int t = gl; t < n_here; t += G) { // on their way to L2 while the neighbourhood is staged
+				prefetch_l2(proposals + first + t);
+				prefetch_l2(pos + first + t);
+				prefetch_l2(ori + 9ll * (first + t));
+				prefetch_l2(ori + 9ll * (first + t) + 8);
+			}
 
-		// ---- stage the 27-cell neighbourhood, one column of three cells at a time: all copies in flight, one wait ----
+		// ---- stage this lane's columns of the neighbourhood (three cells each): all copies in flight, one wait ----
 		int total = 0, self_base = 0;
 		const int z0 = wrap_cell(iz - 1, nz), z2 = wrap_cell(iz + 1, nz);
 #pragma unroll 1
-		for(int c = 0; c < 9; c++) {
+		for(int c = gl; c < 9; c += G) {
 			int cx = ix + c / 3 - 1;
 			if(!sc.slab) cx = wrap_cell(cx, sc.nxl); // (slab: an owned layer always has both x neighbours in the held range)
 			const int *cs = cell_start + (cx * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
 			const int b0 = cs[z0], n0 = cs[z0 + 1] - b0, b1 = cs[iz], n01 = n0 + cs[iz + 1] - b1, b2 = cs[z2], n_col = n01 + cs[z2 + 1] - b2;
 			if(c == 4) self_base = total + n0;
 			for(int k = 0; k < n_col; k++, total++)
-				if(total < kNbCap) {
+				if(total < kCap) {
 					const int seg = (k >= n0) + (k >= n01);
 					const int s = k + (seg == 0 ? b0 : (seg == 1 ? b1 - n0 : b2 - n01));
 					__pipeline_memcpy_async(&s_stage[total][tid], posf + s, 8);
 					s_tag[total][tid] = (unsigned char) (c * 3 + seg);
+					if(kOwn) { // FP64 state of a possible bonding partner: towards L2
+						prefetch_l2(pos + s);
+						prefetch_l2(ori + 9ll * s);
+						prefetch_l2(ori + 9ll * s + 8);
+					}
 				}
 		}
 		__pipeline_commit();
-		const bool staged = total <= kNbCap;
+		bool staged = total <= kCap;
+		if(G > 1) {
+#pragma unroll
+			for(int o = G / 2; o > 0; o >>= 1) staged &= (bool) __shfl_xor_sync(gmask, (int) staged, o);
+		}
 		__pipeline_wait_prior(0);
+		if(kOwn) __syncwarp(gmask); // every lane's copies have landed
 
 		for(int t = 0; t < n_here; t++) {
-			const Proposal *pr = proposals + first + t;
+			const Proposal *pr = own_staged ? &os.pr[t] : proposals + first + t;
 			const int pick = pr->pick;
 			const int sp = first + pick;
-			tl.tries++;
+			const double4 *own_pos = own_staged ? &os.pos[pick] : pos + sp;
+			const double *own_ori = own_staged ? os.ori + 9 * pick : ori + 9ll * sp;
+			if(is_owner) tl.tries++;
 			if(!staged) { // neighbourhood larger than the staging area (dense packing): serial FP64 path
-				trial_serial(sc, cell_start, pos, ori, posf, pr, cell, ix, iy, iz, sp, tl);
+				if(is_owner) trial_serial(sc, cell_start, pos, ori, posf, proposals + first + t, cell, ix, iy, iz, sp, tl);
 				continue;
 			}
 			const double dx = pr->dx, dy = pr->dy, dz = pr->dz;
-			const double4 p4 = pos[sp];
+			const double4 p4 = *own_pos;
 			const Vec3 p_old = {p4.x, p4.y, p4.z};
 			const Vec3 p_new = {__dadd_rn(p4.x, dx), __dadd_rn(p4.y, dy), __dadd_rn(p4.z, dz)};
 			int cx, cy, cz;
 			if(cell_index(sc, p_new.x, p_new.y, p_new.z, cx, cy, cz) != cell) { // would leave its cell
-				tl.conf++;
+				if(is_owner) tl.conf++;
 				continue;
 			}
 			const unsigned long long Wfix = (unsigned long long) pr->wfix;
-			tl.wt += Wfix;
-			const int j_self = self_base + pick;
+			if(is_owner) tl.wt += Wfix;
+			const int j_self = self_base + pick; // meaningful on the owner lane only
 			float fox, foy, foz;
-			shadow_position(s_stage[j_self][tid], s_off[13], ux, uy, uz, fox, foy, foz);
+			shadow_position(s_stage[is_owner ? j_self : 0][tid], s_off[13], ux, uy, uz, fox, foy, foz);
+			if(G > 1) {
+				fox = __shfl_sync(gmask, fox, owner_lane);
+				foy = __shfl_sync(gmask, foy, owner_lane);
+				foz = __shfl_sync(gmask, foz, owner_lane);
+			}
 			const float fnx = fox + (float) dx, fny = foy + (float) dy, fnz = foz + (float) dz;
 
 			// ---- 1. FP32 distance screen over the staged neighbourhood ---------------------
-			s_tag[j_self][tid] = (unsigned char) kFarCode; // the moved particle itself: out of everybody's range
+			if(is_owner) s_tag[j_self][tid] = (unsigned char) kFarCode; // the moved particle itself: out of everybody's range
 			int n_cand = 0;
 			bool ovl = false;
 			for(int j = 0; j < total; j++) {
@@ -165,12 +221,13 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
 				const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
 				ovl |= d2n < core_lo;
-				if(fminf(d2o, d2n) < thr) s_cand[n_cand++][tid] = (unsigned char) j; // n_cand < total <= kCandCap
+				if(fminf(d2o, d2n) < thr) s_cand[n_cand++][tid] = (unsigned char) j; // n_cand <= total <= kCap
 			}
-			s_tag[j_self][tid] = 13;
-			tl.checks += 2ull * (unsigned long long) (total - 1);
+			if(is_owner) s_tag[j_self][tid] = 13;
+			tl.checks += 2ull * (unsigned long long) (total - (is_owner ? 1 : 0));
+			if(G > 1) ovl = __any_sync(gmask, ovl);
 			if(ovl) { // overlapping beyond any FP32 doubt: rejected whatever the bonds (MC.c:296-299, 332)
-				tl.ovl++;
+				if(is_owner) tl.ovl++;
 				continue;
 			}
 
@@ -182,7 +239,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			// separations within the band of the hard core -- goes to FP64.
 			double m[9], mn[9];
 #pragma unroll
-			for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
+			for(int k = 0; k < 9; k++) m[k] = own_ori[k];
 #pragma unroll
 			for(int i = 0; i < 3; i++)
 #pragma unroll
@@ -233,14 +290,22 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 					if(d2 >= 1. && d2 < sc.sqr_rcut) b_old += patches_bond_m(sc, d, d2, m, ori + 9ll * sq) ? 1 : 0;
 				}
 			}
+			if(G > 1) { // the group's verdict: any overlap, total bonds of the old and of the new state
+				unsigned packed = (unsigned) b_old | ((unsigned) b_new << 8) | (ovl ? 1u << 16 : 0u);
+#pragma unroll
+				for(int o = G / 2; o > 0; o >>= 1) packed += __shfl_xor_sync(gmask, packed, o);
+				b_old = (int) (packed & 0xffu);
+				b_new = (int) ((packed >> 8) & 0xffu);
+				ovl = (packed >> 16) != 0u;
+			}
 			if(ovl) { // hard-core overlap: rejected whatever the bonds (MC.c:296-299, 332)
-				tl.ovl++;
+				if(is_owner) tl.ovl++;
 				continue;
 			}
 
 			// ---- 4. Metropolis (MC.c:332-339) ------------------------------------------------
 			const int dE = b_old - b_new; // energy = -bonds
-			if(dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
+			if(is_owner && (dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1])) {
 				double *p = reinterpret_cast<double *>(pos + sp); // x, y, z; the id in .w stays
 				p[0] = p_new.x;
 				p[1] = p_new.y;
@@ -250,10 +315,16 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				s_stage[j_self][tid] = moved;
 #pragma unroll
 				for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
+				if(own_staged) {
+					os.pos[pick] = make_double4(p_new.x, p_new.y, p_new.z, p4.w);
+#pragma unroll
+					for(int k = 0; k < 9; k++) os.ori[9 * pick + k] = mn[k];
+				}
 				tl.dbonds += b_new - b_old;
 				tl.acc++;
 				tl.wa += Wfix;
 			}
+			if(G > 1) __syncwarp(gmask); // the other lanes read the moved particle's new state in the next trials
 		}
 	}
 
@@ -292,14 +363,26 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 	}
 }
 
-// range: device pointer to {first work item, one past the last work item}
-int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
+template<int G>
+static void launch_cells_g(const SimConst &sc, const int *range, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
 		double *ori, Counters *counters, cudaStream_t st) {
-	if(max_items < 1) max_items = 1;
-	long long blocks = (max_items + kCellThreads - 1) / kCellThreads;
-	const long long cap = 148ll * 4 * 8; // a few waves of resident blocks; threads stride over the occupancy-sorted list
+	constexpr int groups = kCellThreads / G;
+	long long blocks = (max_items + groups - 1) / groups;
+	const long long cap = 148ll * 4 * 8; // a few waves of resident blocks; groups stride over the occupancy-sorted list
 	if(blocks > cap) blocks = cap;
-	k_sweep_cells<<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters);
+	k_sweep_cells<G><<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters);
+}
+
+// range: device pointer to {first work item, one past the last work item}; lanes: 1, 2, 4 or 8 lanes per cell
+int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, int lanes, const CellBuffers &cb, const Proposal *proposals,
+		double4 *pos, double *ori, Counters *counters, cudaStream_t st) {
+	if(max_items < 1) max_items = 1;
+	switch(lanes) {
+	case 8: launch_cells_g<8>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
+	case 4: launch_cells_g<4>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
+	case 2: launch_cells_g<2>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
+	default: launch_cells_g<1>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
+	}
 	return 1;
 }
 

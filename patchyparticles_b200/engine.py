@@ -28,7 +28,7 @@ class Params(C.Structure):
                 ("P", C.c_double), ("rescale_factor_max", C.c_double), ("Lx_move", C.c_int),
                 ("Lx_change_max", C.c_double), ("Lyz_min", C.c_double), ("Lyz_max", C.c_double),
                 ("Lx_reference_sign", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
-                ("lanes_per_cell", C.c_int), ("use_graph", C.c_int), ("cells_max_occupancy", C.c_int),
+                ("lanes_per_cell", C.c_int), ("cell_lanes", C.c_int), ("cells_max_occupancy", C.c_int),
                 ("shift_every", C.c_int)]
 
 
@@ -55,7 +55,7 @@ ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy",
                "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats", "pp_slab_setup", "pp_slab_range",
                "pp_slab_sweep_begin", "pp_slab_outbox", "pp_slab_inbox", "pp_slab_sweep_rebuild", "pp_slab_pass_block",
                "pp_slab_halo", "pp_slab_sweep_end", "pp_slab_download", "pp_slab_peer_export", "pp_slab_peer_connect",
-               "pp_slab_refresh", "pp_slab_peer_close"]
+               "pp_slab_refresh", "pp_slab_peer_close", "pp_slab_sweeps"]
 
 
 def load_library():
@@ -104,6 +104,7 @@ def load_library():
     L.pp_slab_peer_connect.argtypes = [H, C.c_char_p, C.c_char_p]
     L.pp_slab_refresh.argtypes = [H, C.c_int]
     L.pp_slab_peer_close.argtypes = [H]
+    L.pp_slab_sweeps.argtypes = [H, C.c_int, PI]
     L.pp_slab_download.argtypes = [H, PI, _ip, _dp, _dp]
     _lib = L
     return L
@@ -118,7 +119,7 @@ class Engine:
 
     def __init__(self, ensemble=NVT, temperature=0.1, disp_max=0.1, theta_max=0.1, kf_delta=0.119, kf_cosmax=0.98,
                  P=0.0, rescale_factor_max=0.0, Lx_move=0, Lx_change_max=0.0, Lyz_min=0.0, Lyz_max=0.0,
-                 Lx_reference_sign=1, seed=12345, device=0, lanes_per_cell=0, use_graph=0, shift_every=0,
+                 Lx_reference_sign=1, seed=12345, device=0, lanes_per_cell=0, cell_lanes=0, shift_every=0,
                  cells_max_occupancy=-1):
         self.L = load_library()
         p = Params()
@@ -127,7 +128,7 @@ class Engine:
         p.kf_delta, p.kf_cosmax, p.P, p.rescale_factor_max = kf_delta, kf_cosmax, P, rescale_factor_max
         p.Lx_move, p.Lx_change_max, p.Lyz_min, p.Lyz_max = Lx_move, Lx_change_max, Lyz_min, Lyz_max
         p.Lx_reference_sign, p.seed, p.device = Lx_reference_sign, seed, device
-        p.lanes_per_cell, p.use_graph, p.shift_every = lanes_per_cell, use_graph, shift_every
+        p.lanes_per_cell, p.cell_lanes, p.shift_every = lanes_per_cell, cell_lanes, shift_every
         p.cells_max_occupancy = cells_max_occupancy
         self.params = p
         self.h = C.c_void_p()
@@ -273,6 +274,12 @@ class Engine:
 
     def slab_refresh(self, side):
         self._check(self.L.pp_slab_refresh(self.h, int(side)))
+
+    def slab_sweeps(self, max_sweeps):
+        """-> sweeps done before the next grid shift (peer-memory halo refresh only)"""
+        done = C.c_int(0)
+        self._check(self.L.pp_slab_sweeps(self.h, int(max_sweeps), C.byref(done)))
+        return int(done.value)
 
     def slab_peer_close(self):
         self._check(self.L.pp_slab_peer_close(self.h))

@@ -198,30 +198,48 @@ class SlabEngine:
             raise RuntimeError(f"rank {self.rank}: halo populations differ across a slab boundary: right halo {halo_r} vs owner {from_r}, "
                                f"left halo {halo_l} vs owner {from_l}")
 
-    def sweep(self, nsteps=1, sync=True):
+    def _migrate(self):
+        """Start of a shift period: particles change owner, halos are rebuilt from records (send/recv)."""
         e, dev = self.eng, self.device
-        for _ in range(int(nsteps)):
+        (pl, nl), (pr, nr) = e.slab_outbox(0), e.slab_outbox(1)
+        _dbg(self.rank, "exchange: to left", nl, "to right", nr)
+        n_from_l, n_from_r = exchange_counts(self.rank, self.world, nl, nr, dev)
+        _dbg(self.rank, "exchange: from left", n_from_l, "from right", n_from_r)
+        il, ir = e.slab_inbox(0, n_from_l), e.slab_inbox(1, n_from_r)
+        exchange_with_neighbours(
+            self.rank, self.world,
+            [device_view(pl, RECORD_DOUBLES * nl, torch.float64, dev)], [device_view(pr, RECORD_DOUBLES * nr, torch.float64, dev)],
+            [device_view(il, RECORD_DOUBLES * n_from_l, torch.float64, dev)], [device_view(ir, RECORD_DOUBLES * n_from_r, torch.float64, dev)])
+        e.slab_sweep_rebuild()
+        _dbg(self.rank, "rebuilt", e.slab_range())
+        self._halo_cache = [None, None]
+        self._rebuilds += 1
+        if self._rebuilds <= 4 or self._rebuilds % 16 == 0 or PARANOID:  # the check costs a host synchronisation
+            self._check_halo_counts()
+
+    def sweep(self, nsteps=1, sync=True):
+        e = self.eng
+        left = int(nsteps)
+        while left > 0:
             if e.slab_sweep_begin():
-                (pl, nl), (pr, nr) = e.slab_outbox(0), e.slab_outbox(1)
-                _dbg(self.rank, "exchange: to left", nl, "to right", nr)
-                n_from_l, n_from_r = exchange_counts(self.rank, self.world, nl, nr, dev)
-                _dbg(self.rank, "exchange: from left", n_from_l, "from right", n_from_r)
-                il, ir = e.slab_inbox(0, n_from_l), e.slab_inbox(1, n_from_r)
-                exchange_with_neighbours(
-                    self.rank, self.world,
-                    [device_view(pl, RECORD_DOUBLES * nl, torch.float64, dev)], [device_view(pr, RECORD_DOUBLES * nr, torch.float64, dev)],
-                    [device_view(il, RECORD_DOUBLES * n_from_l, torch.float64, dev)], [device_view(ir, RECORD_DOUBLES * n_from_r, torch.float64, dev)])
-                e.slab_sweep_rebuild()
-                _dbg(self.rank, "rebuilt", e.slab_range())
-                self._halo_cache = [None, None]
-                self._rebuilds += 1
-                if self._rebuilds <= 4 or self._rebuilds % 16 == 0 or PARANOID:  # the check costs a host synchronisation
-                    self._check_halo_counts()
-            e.slab_pass_block(0)
-            self._halo_refresh(0)
-            e.slab_pass_block(1)
-            self._halo_refresh(1)
-            e.slab_sweep_end()
+                self._migrate()
+            if self.peer_halo:  # the library runs on by itself until the next grid shift
+                done = 1
+                e.slab_pass_block(0)
+                e.slab_refresh(0)
+                e.slab_pass_block(1)
+                e.slab_refresh(1)
+                e.slab_sweep_end()
+                if left > 1:
+                    done += e.slab_sweeps(left - 1)
+            else:
+                done = 1
+                e.slab_pass_block(0)
+                self._halo_refresh(0)
+                e.slab_pass_block(1)
+                self._halo_refresh(1)
+                e.slab_sweep_end()
+            left -= done
         if sync:
             e.sync()
 

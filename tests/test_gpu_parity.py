@@ -119,13 +119,18 @@ def test_total_bonds_vs_port(pp, oracle, N, rho, delta, cosmax):
     e.close()
 
 
-@pytest.mark.parametrize("lanes", [0, 1, 4, 8, 16, 32])
-def test_sweep_matches_port(pp, oracle, lanes):
-    """The CUDA sweep and the serial restatement of the same algorithm give the same trajectory."""
+@pytest.mark.parametrize("lanes,cell_lanes,cmo", [(0, 0, -1), (0, 1, 1), (0, 2, 2), (0, 1, 0), (1, 1, -1), (1, 2, -1), (1, 4, -1), (1, 8, -1),
+                                                  (4, 0, -1), (8, 0, -1), (16, 0, -1), (32, 0, -1), (8, 1, 3)])
+def test_sweep_matches_port(pp, oracle, lanes, cell_lanes, cmo):
+    """The CUDA sweep and the serial restatement of the same algorithm give the same trajectory, whichever
+    kernel runs it: tile kernel of any width (lanes 4..32), thread-per-cell kernel with 1..8 lanes per cell, and the
+    hybrid routing (cmo: cells with at most that many particles on the thread-per-cell kernel, the others on its
+    8-lane latency configuration or, with an explicit tile width, on the tile kernel)."""
     g = load_golden("gen2000_rho0.5")
     delta, cosmax, T = 0.25, 0.8, 0.15  # plenty of bonds
     port = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
-    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T, disp_max=0.2, theta_max=0.3, seed=99, lanes_per_cell=lanes)
+    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T, disp_max=0.2, theta_max=0.3, seed=99, lanes_per_cell=lanes, cell_lanes=cell_lanes,
+                  cells_max_occupancy=cmo)
     e.upload(g["box"], g["r"], g["orient"])
     bonds, _ = e.total_bonds()
     pb, _ = port.total_bonds()
