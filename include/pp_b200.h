@@ -180,6 +180,8 @@ int pp_slab_peer_export(pp_handle *h, void *ipc_handle_64);
 int pp_slab_peer_connect(pp_handle *h, const void *left_handle_64, const void *right_handle_64);
 int pp_slab_refresh(pp_handle *h, int side);
 int pp_slab_peer_close(pp_handle *h);
+/* start of a shift period over peer memory: pp_slab_sweep_begin + record exchange + pp_slab_sweep_rebuild in one call */
+int pp_slab_migrate(pp_handle *h, int *migrated);
 /* whole sweeps over peer memory until max_sweeps are done or the next grid shift needs pp_slab_sweep_begin */
 int pp_slab_sweeps(pp_handle *h, int max_sweeps, int *done);
 int pp_slab_sweep_end(pp_handle *h);

@@ -94,7 +94,8 @@ struct pp_handle {
 	int N_global;        // particles of the whole system
 	double *outbox[2], *inbox[2]; // migration / halo records (13 doubles each) to / from the left (0) and right (1) neighbour
 	int cap_records;
-	int *d_slab_counts;  // keep, left, right, error
+	int *d_slab_counts;  // keep, left, right, error, received from the left, received from the right, (2 spare)
+	int *h_slab_ints;    // pinned: 8 ints read back per rebuild
 	int keep_count, out_count[2], in_count[2];
 	double pending_shift[3];
 	bool slab_pending;   // a classify has been done and waits for pp_slab_sweep_rebuild
@@ -107,7 +108,7 @@ struct pp_handle {
 	long long mbox_cap;           // particles per mailbox
 	char *peer_mbox[2];           // left / right neighbour's block
 	bool peer_same, peer_connected;
-	unsigned long long halo_epoch[2];
+	unsigned long long halo_epoch[2], mig_epoch;
 	unsigned int *d_push_done;
 	int *d_peer_status;
 
@@ -380,8 +381,9 @@ int launch_passes(pp_handle *h, const SimConst &sc, int first_pass, int n_pass) 
 int slab_after_sort(pp_handle *h) {
 	const int nyz = h->n_side[1] * h->n_side[2];
 	const int idx[7] = {0, nyz, 2 * nyz, (h->nxl - 2) * nyz, (h->nxl - 1) * nyz, h->nxl * nyz, h->n_cells + 1};
-	int val[7];
-	for(int k = 0; k < 7; k++) CUDA_OK(h, cudaMemcpyAsync(&val[k], h->cb.cell_start + idx[k], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	int *val = h->h_slab_ints; // one gather kernel + one copy into pinned memory
+	launch_gather_ints(h->cb.cell_start, idx, 7, h->d_slab_counts + 8, h->stream);
+	CUDA_OK(h, cudaMemcpyAsync(val, h->d_slab_counts + 8, 7 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CUDA_OK(h, cudaStreamSynchronize(h->stream));
 	for(int k = 0; k < 6; k++) h->layer_slots[k] = val[k];
 	h->N = val[5]; // everything before the trash cell
@@ -681,6 +683,7 @@ int pp_destroy(pp_handle *h) {
 		cudaFree(h->inbox[k]);
 	}
 	cudaFree(h->d_slab_counts);
+	cudaFreeHost(h->h_slab_ints);
 	peer_release(h);
 	cudaFreeHost(h->h_counters);
 	if(h->ev0) cudaEventDestroy(h->ev0);
@@ -749,7 +752,8 @@ int pp_upload(pp_handle *h, int N, const double *box, const double *r, const dou
 			CUDA_OK(h, cudaMalloc(&h->outbox[k], sizeof(double) * 13 * (size_t) h->cap_records));
 			CUDA_OK(h, cudaMalloc(&h->inbox[k], sizeof(double) * 13 * (size_t) h->cap_records));
 		}
-		if(h->d_slab_counts == nullptr) CUDA_OK(h, cudaMalloc(&h->d_slab_counts, 4 * sizeof(int)));
+		if(h->d_slab_counts == nullptr) CUDA_OK(h, cudaMalloc(&h->d_slab_counts, 16 * sizeof(int)));
+		if(h->h_slab_ints == nullptr) CUDA_OK(h, cudaMallocHost(&h->h_slab_ints, 8 * sizeof(int)));
 		h->slab_pending = false;
 	}
 	if(ensure_state(h, (size_t) N)) return 1;
@@ -1169,7 +1173,7 @@ int pp_slab_peer_export(pp_handle *h, void *ipc_handle_64) {
 	peer_release(h);
 	h->mbox_cap = h->cap_records;
 	h->mbox_stride = ((size_t) h->mbox_cap * 112 + 255) / 256 * 256;
-	const size_t bytes = 2 * h->mbox_stride + 256;
+	const size_t bytes = 4 * h->mbox_stride + 256; // halo from-left, halo from-right, migration from-left, migration from-right, flags
 	CUDA_OK(h, cudaMalloc(&h->mbox, bytes));
 	CUDA_OK(h, cudaMemset(h->mbox, 0, bytes));
 	CUDA_OK(h, cudaMalloc(&h->d_push_done, sizeof(unsigned int)));
@@ -1177,6 +1181,7 @@ int pp_slab_peer_export(pp_handle *h, void *ipc_handle_64) {
 	CUDA_OK(h, cudaMalloc(&h->d_peer_status, sizeof(int)));
 	CUDA_OK(h, cudaMemset(h->d_peer_status, 0, sizeof(int)));
 	h->halo_epoch[0] = h->halo_epoch[1] = 0;
+	h->mig_epoch = 0;
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 bytes");
 	cudaIpcMemHandle_t mh;
 	CUDA_OK(h, cudaIpcGetMemHandle(&mh, h->mbox));
@@ -1219,8 +1224,8 @@ int pp_slab_refresh(pp_handle *h, int side) {
 	// the neighbour's mailbox for data coming from me: its from-right box (1) when I am its right neighbour (side 0)
 	const int box = side == 0 ? 1 : 0;
 	char *peer = h->peer_mbox[side == 0 ? 0 : 1];
-	unsigned long long *peer_flags = reinterpret_cast<unsigned long long *>(peer + 2 * h->mbox_stride);
-	const unsigned long long *my_flags = reinterpret_cast<const unsigned long long *>(h->mbox + 2 * h->mbox_stride);
+	unsigned long long *peer_flags = reinterpret_cast<unsigned long long *>(peer + 4 * h->mbox_stride);
+	const unsigned long long *my_flags = reinterpret_cast<const unsigned long long *>(h->mbox + 4 * h->mbox_stride);
 	double4 *pos = h->pos[h->cp];
 	double *ori = h->ori[h->co];
 	prof_begin(h);
@@ -1230,6 +1235,57 @@ int pp_slab_refresh(pp_handle *h, int side) {
 			h->d_peer_status, h->stream);
 	prof_end(h, PP_K_CELLS, nl);
 	CUDA_OK(h, cudaGetLastError());
+	return 0;
+}
+
+// Start of a shift period over peer memory: classify on the new grid, store the outgoing records straight into the
+// neighbours' migration mailboxes, take in what they stored here, rebuild the cells.  One host synchronisation (the
+// counts), no library transfer.  *migrated = 0 when the current period is still running.
+int pp_slab_migrate(pp_handle *h, int *migrated) {
+	if(h == nullptr || migrated == nullptr) return 1;
+	if(!h->peer_connected) return fail(h, "pp_slab_migrate needs the peer-memory connection (pp_slab_peer_connect)");
+	int exchange = 0;
+	CUDA_OK(h, cudaSetDevice(h->device));
+	*migrated = 0;
+	const long long period = h->prm.shift_every;
+	if(h->sweep_grid && h->cells_valid && h->step % period != 0) return 0;
+	const uint64_t epoch = (uint64_t) (h->step / period);
+	uint32_t x[4];
+	philox_host(kTagShift, 0u, (uint32_t) epoch, (uint32_t) ((epoch >> 32) << 8), (uint32_t) h->prm.seed, (uint32_t) (h->prm.seed >> 32), x);
+	for(int k = 0; k < 3; k++) h->pending_shift[k] = unit_from_u32(x[k]) * (h->box[k] / h->n_side[k]);
+	if(ensure_cells_valid(h)) return 1;
+	const SimConst sc_new = make_const(h, h->box, h->pending_shift);
+	const int tp = (h->cp + 2) % 3, to = h->co ^ 1;
+	prof_begin(h);
+	int nl = launch_slab_classify(sc_new, h->layer_slots[1], h->layer_slots[4], h->x0, h->x1 - h->x0, view(h, h->cp, h->co), view(h, tp, to),
+			h->outbox[0], h->outbox[1], h->cap_records, h->d_slab_counts, h->stream);
+	const unsigned long long me = ++h->mig_epoch;
+	char *flags_area[2] = {h->peer_mbox[0] + 4 * h->mbox_stride, h->peer_mbox[1] + 4 * h->mbox_stride};
+	char *my_area = h->mbox + 4 * h->mbox_stride; // 4 flags (u64), then the two migration counts (int)
+	// to the left neighbour: its from-right migration box (3); to the right neighbour: its from-left box (2)
+	nl += launch_records_push(h->outbox[0], h->d_slab_counts, 1, h->cap_records, reinterpret_cast<double *>(h->peer_mbox[0] + 3 * h->mbox_stride),
+			reinterpret_cast<int *>(flags_area[0] + 32) + 1, reinterpret_cast<unsigned long long *>(flags_area[0]) + 3, me, h->d_push_done, h->stream);
+	nl += launch_records_push(h->outbox[1], h->d_slab_counts, 2, h->cap_records, reinterpret_cast<double *>(h->peer_mbox[1] + 2 * h->mbox_stride),
+			reinterpret_cast<int *>(flags_area[1] + 32) + 0, reinterpret_cast<unsigned long long *>(flags_area[1]) + 2, me, h->d_push_done, h->stream);
+	nl += launch_records_pull(reinterpret_cast<const double *>(h->mbox + 2 * h->mbox_stride), reinterpret_cast<const int *>(my_area + 32) + 0,
+			reinterpret_cast<const unsigned long long *>(my_area) + 2, me, h->cap_records, h->inbox[0], h->d_slab_counts + 4, h->d_peer_status, h->stream);
+	nl += launch_records_pull(reinterpret_cast<const double *>(h->mbox + 3 * h->mbox_stride), reinterpret_cast<const int *>(my_area + 32) + 1,
+			reinterpret_cast<const unsigned long long *>(my_area) + 3, me, h->cap_records, h->inbox[1], h->d_slab_counts + 5, h->d_peer_status, h->stream);
+	prof_end(h, PP_K_CELLS, nl);
+	int *c = h->h_slab_ints;
+	CUDA_OK(h, cudaMemcpyAsync(c, h->d_slab_counts, 6 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CUDA_OK(h, cudaStreamSynchronize(h->stream));
+	if(c[3]) return fail(h, "%d particles moved by more than one x layer at a grid shift", c[3]);
+	if(c[1] > h->cap_records || c[2] > h->cap_records) return fail(h, "slab outbox overflow (%d, %d records, capacity %d)", c[1], c[2], h->cap_records);
+	h->keep_count = c[0];
+	h->out_count[0] = c[1];
+	h->out_count[1] = c[2];
+	h->in_count[0] = c[4];
+	h->in_count[1] = c[5];
+	h->slab_pending = true;
+	(void) exchange;
+	if(pp_slab_sweep_rebuild(h)) return 1;
+	*migrated = 1;
 	return 0;
 }
 

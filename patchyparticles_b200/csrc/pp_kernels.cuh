@@ -91,6 +91,11 @@ int launch_slab_unpack(int n, const double *records, int offset, const StateView
 int launch_slab_download(int slot_begin, int slot_end, const StateView &cur, int *ids, double *r, double *orient, cudaStream_t st);
 int launch_halo_push(const double4 *pos, const double *ori, const uint2 *posf, int n, char *peer_mbox, long long cap, unsigned long long *peer_flag,
 		unsigned long long epoch, unsigned int *done, cudaStream_t st);
+int launch_records_push(const double *outbox, const int *counts, int which, int cap, double *peer_box, int *peer_count, unsigned long long *peer_flag,
+		unsigned long long epoch, unsigned int *done, cudaStream_t st);
+int launch_records_pull(const double *mbox, const int *my_count, const unsigned long long *flag, unsigned long long epoch, int cap, double *inbox,
+		int *in_count, int *status, cudaStream_t st);
+int launch_gather_ints(const int *src, const int *idx, int n, int *out, cudaStream_t st);
 int launch_halo_pull(const char *mbox, long long cap, const unsigned long long *flag, unsigned long long epoch, double4 *pos, double *ori, uint2 *posf,
 		int n, int *status, cudaStream_t st);
 

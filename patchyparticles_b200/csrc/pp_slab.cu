@@ -156,6 +156,72 @@ __global__ void __launch_bounds__(256) k_halo_pull(const char *__restrict__ mbox
 	for(long long i = i0; i < 9ll * n; i += stride) ori[i] = __ldcg(mo + i);
 }
 
+// migration records at a grid shift, over the same peer mailboxes: the sender's count travels with the data
+__global__ void __launch_bounds__(256) k_records_push(const double *__restrict__ outbox, const int *__restrict__ counts, int which, int cap,
+		double *mbox /* peer memory */, int *peer_count, unsigned long long *flag /* peer memory */, unsigned long long epoch, unsigned int *done) {
+	int n = counts[which];
+	n = n < cap ? n : cap; // an overflow is reported by the host from the same counts
+	const long long stride = (long long) gridDim.x * blockDim.x, i0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	for(long long i = i0; i < 13ll * n; i += stride) mbox[i] = outbox[i];
+	__threadfence_system();
+	__syncthreads();
+	if(threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+		*done = 0;
+		*peer_count = n;
+		__threadfence_system();
+		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+	}
+}
+
+__global__ void __launch_bounds__(256) k_records_pull(const double *__restrict__ mbox, const int *my_count, const unsigned long long *flag,
+		unsigned long long epoch, int cap, double *__restrict__ inbox, int *__restrict__ in_count, int *status) {
+	if(threadIdx.x == 0) {
+		const unsigned long long t0 = global_timer_ns();
+		for(;;) {
+			unsigned long long v;
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+			if(v >= epoch) break;
+			if(global_timer_ns() - t0 > 20000000000ull) {
+				atomicExch(status, 1);
+				break;
+			}
+			__nanosleep(200);
+		}
+	}
+	__syncthreads();
+	int n = __ldcg(my_count);
+	n = n < 0 ? 0 : (n < cap ? n : cap);
+	const long long stride = (long long) gridDim.x * blockDim.x, i0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+	for(long long i = i0; i < 13ll * n; i += stride) inbox[i] = __ldcg(mbox + i);
+	if(blockIdx.x == 0 && threadIdx.x == 0) *in_count = n;
+}
+
+struct GatherIdx {
+	int idx[8];
+};
+__global__ void k_gather_ints(const int *__restrict__ src, GatherIdx g, int n, int *__restrict__ out) {
+	if(threadIdx.x < n) out[threadIdx.x] = src[g.idx[threadIdx.x]];
+}
+
+int launch_gather_ints(const int *src, const int *idx, int n, int *out, cudaStream_t st) {
+	GatherIdx g;
+	for(int k = 0; k < 8; k++) g.idx[k] = k < n ? idx[k] : 0;
+	k_gather_ints<<<1, 32, 0, st>>>(src, g, n, out);
+	return 1;
+}
+
+int launch_records_push(const double *outbox, const int *counts, int which, int cap, double *peer_box, int *peer_count, unsigned long long *peer_flag,
+		unsigned long long epoch, unsigned int *done, cudaStream_t st) {
+	k_records_push<<<148, 256, 0, st>>>(outbox, counts, which, cap, peer_box, peer_count, peer_flag, epoch, done);
+	return 1;
+}
+
+int launch_records_pull(const double *mbox, const int *my_count, const unsigned long long *flag, unsigned long long epoch, int cap, double *inbox,
+		int *in_count, int *status, cudaStream_t st) {
+	k_records_pull<<<148, 256, 0, st>>>(mbox, my_count, flag, epoch, cap, inbox, in_count, status);
+	return 1;
+}
+
 int launch_halo_push(const double4 *pos, const double *ori, const uint2 *posf, int n, char *peer_mbox, long long cap, unsigned long long *peer_flag,
 		unsigned long long epoch, unsigned int *done, cudaStream_t st) {
 	int blocks = (9 * n + 255) / 256;

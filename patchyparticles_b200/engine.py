@@ -55,7 +55,7 @@ ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy",
                "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats", "pp_slab_setup", "pp_slab_range",
                "pp_slab_sweep_begin", "pp_slab_outbox", "pp_slab_inbox", "pp_slab_sweep_rebuild", "pp_slab_pass_block",
                "pp_slab_halo", "pp_slab_sweep_end", "pp_slab_download", "pp_slab_peer_export", "pp_slab_peer_connect",
-               "pp_slab_refresh", "pp_slab_peer_close", "pp_slab_sweeps"]
+               "pp_slab_refresh", "pp_slab_peer_close", "pp_slab_sweeps", "pp_slab_migrate"]
 
 
 def load_library():
@@ -105,6 +105,7 @@ def load_library():
     L.pp_slab_refresh.argtypes = [H, C.c_int]
     L.pp_slab_peer_close.argtypes = [H]
     L.pp_slab_sweeps.argtypes = [H, C.c_int, PI]
+    L.pp_slab_migrate.argtypes = [H, PI]
     L.pp_slab_download.argtypes = [H, PI, _ip, _dp, _dp]
     _lib = L
     return L
@@ -280,6 +281,12 @@ class Engine:
         done = C.c_int(0)
         self._check(self.L.pp_slab_sweeps(self.h, int(max_sweeps), C.byref(done)))
         return int(done.value)
+
+    def slab_migrate(self):
+        """Start of a shift period over peer memory -> True if the cells were rebuilt."""
+        done = C.c_int(0)
+        self._check(self.L.pp_slab_migrate(self.h, C.byref(done)))
+        return bool(done.value)
 
     def slab_peer_close(self):
         self._check(self.L.pp_slab_peer_close(self.h))

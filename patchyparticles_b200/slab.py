@@ -211,7 +211,10 @@ class SlabEngine:
             [device_view(pl, RECORD_DOUBLES * nl, torch.float64, dev)], [device_view(pr, RECORD_DOUBLES * nr, torch.float64, dev)],
             [device_view(il, RECORD_DOUBLES * n_from_l, torch.float64, dev)], [device_view(ir, RECORD_DOUBLES * n_from_r, torch.float64, dev)])
         e.slab_sweep_rebuild()
-        _dbg(self.rank, "rebuilt", e.slab_range())
+        self._after_rebuild()
+
+    def _after_rebuild(self):
+        _dbg(self.rank, "rebuilt", self.eng.slab_range())
         self._halo_cache = [None, None]
         self._rebuilds += 1
         if self._rebuilds <= 4 or self._rebuilds % 16 == 0 or PARANOID:  # the check costs a host synchronisation
@@ -221,7 +224,10 @@ class SlabEngine:
         e = self.eng
         left = int(nsteps)
         while left > 0:
-            if e.slab_sweep_begin():
+            if self.peer_halo:
+                if e.slab_migrate():
+                    self._after_rebuild()
+            elif e.slab_sweep_begin():
                 self._migrate()
             if self.peer_halo:  # the library runs on by itself until the next grid shift
                 done = 1
