@@ -393,19 +393,26 @@ def main():
     n_local = eng.slab_range()[3] if sharded else N
     peak, peak_src = measured_peaks()
     sweep_launches, sweep_ms = stats["sweep"]
-    per_launch_ms = sweep_ms / max(sweep_launches, 1)
+    n_passes = 8 * n_prof
+    # hybrid routing: two concurrent launches per colour pass (sparse cells / crowded cells), timed together
+    launches_per_pass = max(1, round(sweep_launches / n_passes))
+    per_launch_ms = sweep_ms / n_passes
+    sweep_kernel = "k_sweep_pass" if launches_per_pass == 1 else "k_sweep_cells<1> || k_sweep_cells<8> (the two concurrent launches of a colour pass)"
     n_owned = N / world if sharded else N
     bytes_per_launch = SWEEP_BYTES_PER_ATTEMPT * n_owned / 8.0
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     cell_builds = max(stats["cells"][0] // 10, 1)
     kernels = {
-        "sweep_pass": {"launches": sweep_launches, "ms_per_launch": per_launch_ms, "alg_bytes_per_launch": bytes_per_launch, "GBps": achieved},
+        "sweep_pass": {"launches": sweep_launches, "passes": n_passes, "ms_per_launch": per_launch_ms, "alg_bytes_per_launch": bytes_per_launch,
+                       "GBps": achieved},
         "cell_build": {"launches": stats["cells"][0], "builds": cell_builds, "ms_per_build": stats["cells"][1] / cell_builds,
                        "GBps": CELLS_BYTES_PER_PARTICLE * n_local / (stats["cells"][1] / cell_builds * 1e-3) / 1e9},
         "proposals": {"launches": stats["rng"][0], "ms_per_launch": stats["rng"][1] / max(stats["rng"][0], 1)},
         "bond_count": {"launches": stats["bonds"][0], "ms": stats["bonds"][1],
                        "GBps": BONDS_BYTES_PER_PARTICLE * n_owned / (max(stats["bonds"][1], 1e-9) * 1e-3) / 1e9},
     }
+    if sharded:  # pushes into the neighbour's mailbox + pulls (the pull includes waiting for the neighbour)
+        kernels["halo"] = {"launches": stats["halo"][0], "ms_per_sweep": stats["halo"][1] / max(n_prof, 1)}
 
     # invariant after the measured regions: running energy == recount (MC_check_energy)
     b_chk, ov_chk, ok = arm.check_energy()
@@ -448,7 +455,8 @@ def main():
 
     if rank == 0:
         if sharded:
-            par = f"one system in {world} x-slabs, NCCL halo exchange (2 per sweep) + migration every shift period"
+            par = (f"one system in {world} x-slabs; halo refresh (2 per sweep) and migration (every shift period) as stores into the "
+                   "neighbour GPU's memory over NVLink (CUDA IPC mailboxes, device-side flags)")
         else:
             par = "single GPU" if world == 1 else f"{world} independent replicas"
         line = {
@@ -461,7 +469,7 @@ def main():
             "value_l2_warm": K * attempts_per_step / (warm_ms * 1e-3),
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": SWEEP_TRAFFIC_BYTES.get(w),
-                         "kernel": "k_sweep_pass", "peak_source": peak_src + " (of measured)",
+                         "kernel": sweep_kernel, "peak_source": peak_src + " (of measured)",
                          "note": "algorithmic bytes = 64 B per attempted move (SURVEY 8d); traffic = ncu dram bytes per launch (profiles/); "
                                  "the sweep is latency / L2 bound, not HBM bound"},
             "kernels": kernels,

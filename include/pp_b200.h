@@ -141,7 +141,8 @@ int pp_set_profiling(pp_handle *h, int enable);
 #define PP_K_PROPOSALS 4 /* K5: proposal evaluator */
 #define PP_K_ORTHO 5     /* K6: re-orthonormalise */
 #define PP_K_RNG 6       /* K2a: proposal generation (Philox, rotation matrices) */
-#define PP_K_CLASSES 7
+#define PP_K_HALO 7      /* slab decomposition: halo refresh and migration over peer memory (includes waiting for the neighbour) */
+#define PP_K_CLASSES 8
 int pp_kernel_stats(pp_handle *h, int kclass, long long *launches, double *ms_total);
 int pp_reset_kernel_stats(pp_handle *h);
 

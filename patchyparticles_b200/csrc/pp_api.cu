@@ -1233,7 +1233,7 @@ int pp_slab_refresh(pp_handle *h, int side) {
 			h->d_push_done, h->stream);
 	nl += launch_halo_pull(h->mbox + box * h->mbox_stride, h->mbox_cap, my_flags + box, epoch, pos + rb, ori + 9ll * rb, h->cb.posf + rb, re - rb,
 			h->d_peer_status, h->stream);
-	prof_end(h, PP_K_CELLS, nl);
+	prof_end(h, PP_K_HALO, nl);
 	CUDA_OK(h, cudaGetLastError());
 	return 0;
 }
@@ -1244,7 +1244,6 @@ int pp_slab_refresh(pp_handle *h, int side) {
 int pp_slab_migrate(pp_handle *h, int *migrated) {
 	if(h == nullptr || migrated == nullptr) return 1;
 	if(!h->peer_connected) return fail(h, "pp_slab_migrate needs the peer-memory connection (pp_slab_peer_connect)");
-	int exchange = 0;
 	CUDA_OK(h, cudaSetDevice(h->device));
 	*migrated = 0;
 	const long long period = h->prm.shift_every;
@@ -1259,6 +1258,9 @@ int pp_slab_migrate(pp_handle *h, int *migrated) {
 	prof_begin(h);
 	int nl = launch_slab_classify(sc_new, h->layer_slots[1], h->layer_slots[4], h->x0, h->x1 - h->x0, view(h, h->cp, h->co), view(h, tp, to),
 			h->outbox[0], h->outbox[1], h->cap_records, h->d_slab_counts, h->stream);
+	prof_end(h, PP_K_CELLS, nl);
+	prof_begin(h);
+	nl = 0;
 	const unsigned long long me = ++h->mig_epoch;
 	char *flags_area[2] = {h->peer_mbox[0] + 4 * h->mbox_stride, h->peer_mbox[1] + 4 * h->mbox_stride};
 	char *my_area = h->mbox + 4 * h->mbox_stride; // 4 flags (u64), then the two migration counts (int)
@@ -1271,7 +1273,7 @@ int pp_slab_migrate(pp_handle *h, int *migrated) {
 			reinterpret_cast<const unsigned long long *>(my_area) + 2, me, h->cap_records, h->inbox[0], h->d_slab_counts + 4, h->d_peer_status, h->stream);
 	nl += launch_records_pull(reinterpret_cast<const double *>(h->mbox + 3 * h->mbox_stride), reinterpret_cast<const int *>(my_area + 32) + 1,
 			reinterpret_cast<const unsigned long long *>(my_area) + 3, me, h->cap_records, h->inbox[1], h->d_slab_counts + 5, h->d_peer_status, h->stream);
-	prof_end(h, PP_K_CELLS, nl);
+	prof_end(h, PP_K_HALO, nl);
 	int *c = h->h_slab_ints;
 	CUDA_OK(h, cudaMemcpyAsync(c, h->d_slab_counts, 6 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -1283,7 +1285,6 @@ int pp_slab_migrate(pp_handle *h, int *migrated) {
 	h->in_count[0] = c[4];
 	h->in_count[1] = c[5];
 	h->slab_pending = true;
-	(void) exchange;
 	if(pp_slab_sweep_rebuild(h)) return 1;
 	*migrated = 1;
 	return 0;

@@ -14,7 +14,7 @@ N_MOVES = 8
 ROTO_TRASL, VOLUME, LX = 0, 6, 7
 NVT, NPT = 0, 5
 K_CELLS, K_SWEEP, K_BONDS, K_RESCALE, K_PROPOSALS, K_ORTHO, K_RNG = range(7)
-KERNEL_CLASSES = ["cells", "sweep", "bonds", "rescale", "proposals", "ortho", "rng"]
+KERNEL_CLASSES = ["cells", "sweep", "bonds", "rescale", "proposals", "ortho", "rng", "halo"]
 
 
 class LibraryMissing(RuntimeError):
