@@ -58,10 +58,13 @@ typedef struct pp_params {
 	int Lx_reference_sign;      /* 1: reproduce exp(+dE/T) of MC.c:562; 0: Metropolis exp(-dE/T) */
 	uint64_t seed;              /* Seed                                             system.c:71-75 */
 	int device;                 /* CUDA device ordinal */
-	int lanes_per_cell;         /* 0 = default (hybrid: sparse cells one thread each, crowded cells one tile each);
-	                               1 = every cell one thread; 4, 8, 16, 32 = every cell one tile of that width */
-	int cell_lanes;             /* lanes per cell of the thread-per-cell sweep kernel: 0 auto, 1, 2, 4, 8 */
-	int cells_max_occupancy;    /* hybrid mode: cells with at most this many particles go to the thread-per-cell kernel; -1 = default (3) */
+	int lanes_per_cell;         /* kernel choice of the sweep.  0 = automatic: by system size, either the tile kernel alone or the
+	                               hybrid routing (sparsely populated cells on the thread-per-cell kernel, crowded ones on its
+	                               8-lane configuration, concurrently); 1 = thread-per-cell kernel wherever a cell fits it;
+	                               4, 8, 16, 32 = tile kernel of that width (for the crowded cells if cells_max_occupancy > 0) */
+	int cell_lanes;             /* lanes per cell of the thread-per-cell kernel for the sparsely populated cells: 0 = 1, or 1, 2, 4, 8 */
+	int cells_max_occupancy;    /* hybrid routing: cells with at most this many particles go to the thread-per-cell kernel;
+	                               -1 = automatic (3 for N >= 800k, 2 for N >= 300k, else 0), 0 = tile kernel only */
 	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
 } pp_params;
 
@@ -170,7 +173,7 @@ int pp_slab_inbox(pp_handle *h, int side, int count, void **dev);
 int pp_slab_sweep_rebuild(pp_handle *h);
 int pp_slab_pass_block(pp_handle *h, int cx);
 int pp_slab_halo(pp_handle *h, int side, int recv, void **pos, void **ori, void **posf, int *count);
- /* Halo refresh over peer memory, for engines on the GPUs of one NVLink / NVSwitch node (replaces the
+/* Halo refresh over peer memory, for engines on the GPUs of one NVLink / NVSwitch node (replaces the
  * library transfers of the pp_slab_halo slices).  Every engine exports a mailbox block as a 64-byte
  * cudaIpcMemHandle_t after pp_upload, the driver hands each engine the handles of its left and right
  * neighbour, and pp_slab_refresh(side) then (1) stores the engine's first (side 0) / last (side 1) owned
