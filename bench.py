@@ -99,9 +99,9 @@ def _run_ref(binary, workdir, rrr, steps, T):
     return time.perf_counter() - t0, p.returncode
 
 
-def time_reference(w, sweeps):
+def time_reference(w, sweeps, warmup=0):
     """wall(sweeps) - wall(0 sweeps) of the unmodified reference binary, single thread (the reference
-    has no threads: main.c:26-143)."""
+    has no threads: main.c:26-143); `warmup` steps are run once before, untimed (page cache, CPU clocks)."""
     N, rho, T = WORKLOADS[w]
     rrr = reference_rrr(N, rho)
     if rrr is None:
@@ -127,6 +127,8 @@ def time_reference(w, sweeps):
             break
         if kind_flags is None:
             return None
+        if warmup > 0:
+            _run_ref(binary, d, rrr, warmup, T)
         t_run, rc = _run_ref(binary, d, rrr, sweeps, T)
         if rc != 0:
             return None
@@ -148,13 +150,14 @@ def run_reference_arm(args, w):
         return 0
     N = WORKLOADS[w][0]
     sweeps = max(1, min(args.steps, reference_sample_sweeps(w, 40.0)))
-    res = time_reference(w, sweeps)
+    warm = max(0, min(args.warmup, 3, sweeps))  # a separate, untimed run of the binary
+    res = time_reference(w, sweeps, warm)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref reference binaries missing or not runnable on this host"}))
         return 0
     line = {
         "impl": "reference", "metric": "MC roto-translation attempts/sec", "value": res["value"], "unit": "attempts/s",
-        "n_gpus": args.gpus, "steps": sweeps, "warmup": 0, "ms_per_step": 1e3 * res["seconds"] / sweeps,
+        "n_gpus": args.gpus, "steps": sweeps, "warmup": warm, "ms_per_step": 1e3 * res["seconds"] / sweeps,
         "higher_is_better": True, "scaling": "strong" if WORKLOADS[w][0] > 500000 else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": workload_name(w), "N_total": N},
         "cpu_baseline": {"value": res["value"], "unit": "attempts/s", "cores": 1, "kind": "reference",
