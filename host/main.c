@@ -38,7 +38,12 @@ typedef struct {
 	FILE *log, *energy, *density, *acc, *boxshape;
 	llint start_from, print_every, save_every;
 	char conf_folder[512], conf_last[512];
+	int print_bonds; /* Print_bonds / Bonds_folder (output.c:88-99) */
+	char bonds_folder[512];
+	int *bond_counts, *bond_neighbours;
 } host_output;
+
+#define PP_HOST_MAX_BONDS 16 /* neighbours listed per particle; four patches of half-angle acos(0.98) hold far fewer */
 
 static void log_msg(host_output *out, const char *fmt, ...) {
 	va_list ap;
@@ -87,6 +92,31 @@ static void save_configuration(host_output *out, pp_handle *h, int N, llint step
 }
 
 /* output_print (output.c:119-211) */
+/* output_print_bonds (output.c:213-268): N, then two lines per particle -- "index n_bonds" and the indices of the bonded
+ * neighbours, each followed by a blank (possibly an empty line).  The reference builds the second line with an
+ * overlapping sprintf (output.c:250, undefined behaviour); here it is simply the list, cell by cell. */
+static void print_bonds(host_output *out, pp_handle *h, int N, llint step) {
+	char name[1100];
+	snprintf(name, sizeof(name), "%s/bonds_%lld.dat", out->bonds_folder, step);
+	if(pp_bond_lists(h, PP_HOST_MAX_BONDS, out->bond_counts, out->bond_neighbours)) {
+		fprintf(stderr, "%s\n", pp_last_error(h));
+		exit(1);
+	}
+	FILE *f = fopen(name, "w");
+	if(f == NULL) {
+		fprintf(stderr, "Bonds file '%s' is not writable\n", name);
+		exit(1);
+	}
+	fprintf(f, "%d\n", N);
+	for(int i = 0; i < N; i++) {
+		fprintf(f, "%d %d\n", i, out->bond_counts[i]);
+		const int n = out->bond_counts[i] < PP_HOST_MAX_BONDS ? out->bond_counts[i] : PP_HOST_MAX_BONDS;
+		for(int k = 0; k < n; k++) fprintf(f, "%d ", out->bond_neighbours[(size_t) i * PP_HOST_MAX_BONDS + k]);
+		fprintf(f, "\n");
+	}
+	fclose(f);
+}
+
 static void print_observables(host_output *out, pp_handle *h, const pp_params *prm, llint step) {
 	pp_observables o;
 	PP_CALL(out, h, pp_get_observables(h, &o, 1)); /* counters are reset after each print (output.c:189) */
@@ -180,6 +210,13 @@ int main(int argc, char *argv[]) {
 	pph_get_double(in, "KF_cosmax", &prm.kf_cosmax, 1);
 	log_msg(&out, "Patch parameters: cosmax = %lf, delta = %lf\n", prm.kf_cosmax, prm.kf_delta);
 	if(dynamics != 0) die(&out, "Dynamics %d not supported on the GPU path (only 0, roto-translations; VMMC/AVB stay on the CPU reference)\n", dynamics);
+	pph_get_int(in, "Print_bonds", &out.print_bonds, 0);
+	if(out.print_bonds) { /* output.c:88-99 */
+		if(prm.ensemble != PP_NVT) die(&out, "The printing of bonds is unavailable in non-canonical ensembles");
+		pph_get_string(in, "Bonds_folder", out.bonds_folder, sizeof(out.bonds_folder), 1);
+		if(access(out.bonds_folder, W_OK) != 0)
+			die(&out, "Cannot create files in directory '%s': please make sure that the directory exists and it is writable\n", out.bonds_folder);
+	}
 	if(prm.ensemble != PP_NVT && prm.ensemble != PP_NPT)
 		die(&out, "Ensemble %d not supported on the GPU path (0 = NVT, 5 = NPT; GC/SUS/BSUS stay on the CPU reference)\n", prm.ensemble);
 	if(prm.ensemble != PP_NVT) {
@@ -235,6 +272,12 @@ int main(int argc, char *argv[]) {
 	if(overlap) die(&out, "Initial configuration contains an overlap, aborting\n");
 	log_msg(&out, "Initial energy: %lf\n", (N > 0) ? -(double) bonds / N : 0.);
 
+	if(out.print_bonds) {
+		out.bond_counts = malloc(sizeof(int) * (size_t) (N > 0 ? N : 1));
+		out.bond_neighbours = malloc(sizeof(int) * (size_t) (N > 0 ? N : 1) * PP_HOST_MAX_BONDS);
+		if(out.bond_counts == NULL || out.bond_neighbours == NULL) die(&out, "out of memory\n");
+	}
+
 	llint steps = 0;
 	pph_get_llint(in, "Steps", &steps, 1);
 	steps += out.start_from;
@@ -244,6 +287,7 @@ int main(int argc, char *argv[]) {
 	while(step < steps && !stop_requested) {
 		if(step % out.print_every == 0) {
 			print_observables(&out, h, &prm, step);
+			if(out.print_bonds) print_bonds(&out, h, N, step);
 			save_configuration(&out, h, N, step, out.conf_last, r, orient);
 			if(step != 0) { /* MC_check_energy + cells_check (main.c:85-87) */
 				llint scratch;
@@ -283,6 +327,8 @@ int main(int argc, char *argv[]) {
 	pp_destroy(h);
 	free(r);
 	free(orient);
+	free(out.bond_counts);
+	free(out.bond_neighbours);
 	fclose(out.energy);
 	fclose(out.acc);
 	if(out.density) fclose(out.density);

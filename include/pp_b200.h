@@ -103,6 +103,11 @@ int pp_download(pp_handle *h, double *r, double *orient);
 int pp_total_bonds(pp_handle *h, long long *bonds, int *overlap);
 /* per-particle bonded-neighbour counts, what Print_bonds reports (output.c:213-268) */
 int pp_bond_counts(pp_handle *h, int *counts);
+/* the two lines output_print_bonds writes per particle (output.c:222-264): counts[i] = number of bonded neighbours of
+ * particle i, neighbours[i * max_per_particle + k] = their indices (first max_per_particle of them, -1 beyond the
+ * count), listed cell by cell in the reference's 27-cell order and by index inside a cell (the reference follows its
+ * linked lists and builds the line with an overlapping sprintf, output.c:250; compare as sets).  neighbours may be NULL. */
+int pp_bond_lists(pp_handle *h, int max_per_particle, int *counts, int *neighbours);
 
 /* do_ensemble x nsteps (main.c:119 -> do_NVT / do_NPT, MC.c:19-29,60-68): each step is N
  * roto-translation attempts (MC_move_rototranslate, MC.c:311-340) as one 8-colour checkerboard

@@ -313,6 +313,35 @@ void ppo_bond_counts(ppo_system *s, int *counts, int *overlaps) {
 	for(i = 0; i < s->N; i++) counts[i] = ppo_particle_bonds(s, i, overlaps + i);
 }
 
+/* the two lines output_print_bonds writes per particle (output.c:222-264): bonded-neighbour count and indices, walking
+ * the 27 cells in the reference's order; no early exit on overlaps (the reference calls MC_interact pair by pair). */
+void ppo_bond_lists(ppo_system *s, int max_nb, int *counts, int *neigh) {
+	int i, j, k, l, idx[3];
+	for(i = 0; i < s->N; i++) {
+		int n = 0;
+		ppo_cell_coords(s->r + 3 * i, s->box, s->n_side, idx);
+		for(j = -1; j < 2; j++) {
+			int cx = (idx[0] + j + s->n_side[0]) % s->n_side[0];
+			for(k = -1; k < 2; k++) {
+				int cy = (idx[1] + k + s->n_side[1]) % s->n_side[1];
+				for(l = -1; l < 2; l++) {
+					int cz = (idx[2] + l + s->n_side[2]) % s->n_side[2];
+					int c = (cx * s->n_side[1] + cy) * s->n_side[2] + cz, a;
+					for(a = s->cell_start[c]; a < s->cell_start[c + 1]; a++) {
+						int q = s->cell_items[a];
+						if(q == i) continue;
+						if(ppo_pair(s->r + 3 * i, s->patches + 12 * i, s->r + 3 * q, s->patches + 12 * q, s->box, s->sqr_rcut, s->kf_cosmax) == 1) {
+							if(neigh != NULL && n < max_nb) neigh[(size_t) i * max_nb + n] = q;
+							n++;
+						}
+					}
+				}
+			}
+		}
+		counts[i] = n;
+	}
+}
+
 /* move particle i between CSR cells (the reference relinks its lists, MC.c:180-206) */
 static void cells_move(ppo_system *s, int i, const double *r_new) {
 	int idx[3];

@@ -60,7 +60,8 @@ void ppo_set_state(ppo_system *s, const double *r, const double *orient, const d
 int ppo_particle_bonds(ppo_system *s, int i, int *overlap);                        /* MC.c:272-309 */
 /* number of bonded PAIRS in the system (energy = -bonds), *overlap = 1 if any pair overlaps */
 long long ppo_total_bonds(ppo_system *s, int *overlap);                            /* main.c:55-61 */
-void ppo_bond_counts(ppo_system *s, int *counts, int *overlaps);                   /* output.c:213-268 */
+void ppo_bond_counts(ppo_system *s, int *counts, int *overlaps);
+void ppo_bond_lists(ppo_system *s, int max_nb, int *counts, int *neigh);                   /* output.c:213-268 */
 
 /* same contract as ref_eval_proposals in ref_harness.c                          MC.c:328-339 */
 void ppo_eval_proposals(ppo_system *s, int n, const int *idx, const double *disp, const double *orient_new,

@@ -156,6 +156,23 @@ void ref_bond_counts(int *counts, int *overlaps) {
 	g_syst.overlap = 0;
 }
 
+/* bonded neighbours of every particle by the reference's own pair function, over ALL pairs (no cells): an
+ * independent statement of what output_print_bonds (output.c:213-268) is meant to list.  O(N^2): test sizes only. */
+void ref_bond_lists(int max_nb, int *counts, int *neigh) {
+	int i, j, onp, onq;
+	for(i = 0; i < g_syst.N; i++) {
+		int n = 0;
+		for(j = 0; j < g_syst.N; j++) {
+			if(j == i) continue;
+			if(MC_interact(&g_syst, g_syst.particles + i, g_syst.particles + j, &onp, &onq) == PATCH_BOND) {
+				if(neigh != NULL && n < max_nb) neigh[(size_t) i * max_nb + n] = j;
+				n++;
+			}
+		}
+		counts[i] = n;
+	}
+}
+
 void ref_rotate(const double *orient_old, const double *axis, double theta, double *orient_new) {
 	matrix o, n;
 	vector a = {axis[0], axis[1], axis[2]};

@@ -803,19 +803,33 @@ int pp_total_bonds(pp_handle *h, long long *bonds, int *overlap) {
 	return 0;
 }
 
-int pp_bond_counts(pp_handle *h, int *counts) {
-	if(h == nullptr) return 1;
+int pp_bond_lists(pp_handle *h, int max_per_particle, int *counts, int *neighbours) {
+	if(h == nullptr || counts == nullptr) return 1;
+	if(neighbours != nullptr && max_per_particle < 1) return fail(h, "pp_bond_lists: max_per_particle must be positive");
+	if(h->slab_world > 1) return fail(h, "pp_bond_lists / pp_bond_counts are single-engine calls");
 	if(h->N == 0) return 0;
+	CUDA_OK(h, cudaSetDevice(h->device));
 	if(ensure_cells_valid(h)) return 1;
 	const SimConst sc = make_const(h, h->box, h->shift);
 	int *d_counts = h->cb.cell_of; // N ints of scratch, rewritten by the next cell build
+	int *d_nb = nullptr;
+	const size_t nb_bytes = sizeof(int) * (size_t) h->N * (size_t) (neighbours ? max_per_particle : 0);
+	if(neighbours) {
+		CUDA_OK(h, cudaMalloc(&d_nb, nb_bytes));
+		CUDA_OK(h, cudaMemsetAsync(d_nb, 0xff, nb_bytes, h->stream)); // unused entries read -1
+	}
 	prof_begin(h);
-	const int nl = launch_bond_counts(sc, h->cb.cell_start, h->pos[h->cp], h->ori[h->co], h->pid[h->co], d_counts, h->stream);
+	const int nl = launch_bond_counts(sc, h->cb.cell_start, h->pos[h->cp], h->ori[h->co], h->pid[h->co], d_counts, d_nb, max_per_particle, h->stream);
 	prof_end(h, PP_K_BONDS, nl);
-	CUDA_OK(h, cudaMemcpyAsync(counts, d_counts, sizeof(int) * (size_t) h->N, cudaMemcpyDeviceToHost, h->stream));
-	CUDA_OK(h, cudaStreamSynchronize(h->stream));
+	cudaError_t e = cudaMemcpyAsync(counts, d_counts, sizeof(int) * (size_t) h->N, cudaMemcpyDeviceToHost, h->stream);
+	if(e == cudaSuccess && neighbours) e = cudaMemcpyAsync(neighbours, d_nb, nb_bytes, cudaMemcpyDeviceToHost, h->stream);
+	if(e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+	cudaFree(d_nb);
+	if(e != cudaSuccess) return fail(h, "pp_bond_lists: %s", cudaGetErrorString(e));
 	return 0;
 }
+
+int pp_bond_counts(pp_handle *h, int *counts) { return pp_bond_lists(h, 0, counts, nullptr); }
 
 int pp_sweep(pp_handle *h, long long nsteps) {
 	if(h == nullptr) return 1;

@@ -87,11 +87,13 @@ int launch_total_bonds(const SimConst &sc, const int *cell_start, const double4 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-particle bonded-neighbour counts (the numbers output_print_bonds writes, output.c:213-268).
+// Per-particle bonded-neighbour counts and, optionally, the ids of the bonded neighbours (the two lines
+// output_print_bonds writes per particle, output.c:213-268).
 // ---------------------------------------------------------------------------------------------
 template<int G>
 __global__ void __launch_bounds__(kBondThreads) k_bond_counts(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
-		const double4 *__restrict__ pos, const double *__restrict__ ori, const int *__restrict__ pid, int *__restrict__ counts) {
+		const double4 *__restrict__ pos, const double *__restrict__ ori, const int *__restrict__ pid, int *__restrict__ counts,
+		int *__restrict__ neighbours, int max_nb) {
 	constexpr int kTiles = kBondThreads / G;
 	__shared__ Neighbourhood s_nb[kTiles];
 	cg::thread_block block = cg::this_thread_block();
@@ -116,25 +118,36 @@ __global__ void __launch_bounds__(kBondThreads) k_bond_counts(const __grid_const
 			for(int k = 0; k < 9; k++) mp[k] = ori[9ll * sp + k];
 			patches_from(sc.base, mp, pp);
 			int bonds = 0;
-			for(int j = lane; j < total; j += G) {
-				const int sq = neighbour_slot(nb, j);
-				if(sq == sp) continue;
-				bonds += (pair_test(sc, p, pp, pos[sq], ori + 9ll * sq) == 1);
+			const int id_p = pid[sp];
+			for(int j0 = 0; j0 < total; j0 += G) { // whole tile in step: the neighbour ids are written in neighbourhood order
+				const int j = j0 + lane;
+				int sq = -1;
+				bool bonded = false;
+				if(j < total) {
+					sq = neighbour_slot(nb, j);
+					bonded = (sq != sp) && (pair_test(sc, p, pp, pos[sq], ori + 9ll * sq) == 1);
+				}
+				const unsigned hit = tile.ballot(bonded);
+				if(neighbours != nullptr && bonded) {
+					const int at = bonds + __popc(hit & ((1u << lane) - 1u));
+					if(at < max_nb) neighbours[(long long) id_p * max_nb + at] = pid[sq];
+				}
+				bonds += __popc(hit);
 			}
-			bonds = cg::reduce(tile, bonds, cg::plus<int>());
-			if(lane == 0) counts[pid[sp]] = bonds;
+			if(lane == 0) counts[id_p] = bonds;
 		}
 	}
 }
 
-int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, cudaStream_t st) {
+int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, int *neighbours,
+		int max_nb, cudaStream_t st) {
 	constexpr int G = 8;
 	const int tiles_per_block = kBondThreads / G;
 	int blocks = (sc.n_cells + tiles_per_block - 1) / tiles_per_block;
 	const int cap = 148 * 16 * 4;
 	if(blocks > cap) blocks = cap;
 	if(blocks < 1) blocks = 1;
-	k_bond_counts<G><<<blocks, kBondThreads, 0, st>>>(sc, cell_start, pos, ori, pid, counts);
+	k_bond_counts<G><<<blocks, kBondThreads, 0, st>>>(sc, cell_start, pos, ori, pid, counts, neighbours, max_nb);
 	return 1;
 }
 

@@ -71,7 +71,8 @@ int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items
 // K3: full bond count + overlap flag into counters->bonds / counters->overlap (zeroed by the launcher)
 int launch_total_bonds(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, Counters *counters, cudaStream_t st);
 // per-particle bonded-neighbour counts (indexed by particle id)
-int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, cudaStream_t st);
+int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, int *neighbours,
+		int max_nb, cudaStream_t st);
 
 // K4: dst.xyz = src.xyz * factor (or / factor when divide != 0) per axis, id carried over
 int launch_rescale(int N, const double4 *src, double4 *dst, double fx, double fy, double fz, int divide, cudaStream_t st);

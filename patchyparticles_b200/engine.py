@@ -50,7 +50,7 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 # every symbol include/pp_b200.h declares
 ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy", "pp_last_error", "pp_upload",
-               "pp_download", "pp_total_bonds", "pp_bond_counts", "pp_sweep", "pp_sync", "pp_get_observables",
+               "pp_download", "pp_total_bonds", "pp_bond_counts", "pp_bond_lists", "pp_sweep", "pp_sync", "pp_get_observables",
                "pp_check_energy", "pp_eval_proposals", "pp_volume_move", "pp_Lx_move", "pp_set_stream",
                "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats", "pp_slab_setup", "pp_slab_range",
                "pp_slab_sweep_begin", "pp_slab_outbox", "pp_slab_inbox", "pp_slab_sweep_rebuild", "pp_slab_pass_block",
@@ -79,6 +79,7 @@ def load_library():
     L.pp_download.argtypes = [H, _dp, _dp]
     L.pp_total_bonds.argtypes = [H, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.pp_bond_counts.argtypes = [H, _ip]
+    L.pp_bond_lists.argtypes = [H, C.c_int, _ip, _ip]
     L.pp_sweep.argtypes = [H, C.c_longlong]
     L.pp_sync.argtypes = [H]
     L.pp_get_observables.argtypes = [H, C.POINTER(Observables), C.c_int]
@@ -183,6 +184,13 @@ class Engine:
         c = np.zeros(max(self.N, 1), dtype=np.int32)
         self._check(self.L.pp_bond_counts(self.h, c))
         return c[:self.N]
+
+    def bond_lists(self, max_per_particle=8):
+        """-> (counts[N], neighbours[N, max_per_particle]) as output_print_bonds lists them (output.c:213-268); -1 = unused"""
+        c = np.zeros(max(self.N, 1), dtype=np.int32)
+        nb = np.full((max(self.N, 1), int(max_per_particle)), -1, dtype=np.int32)
+        self._check(self.L.pp_bond_lists(self.h, int(max_per_particle), c, nb.reshape(-1)))
+        return c[:self.N], nb[:self.N]
 
     def check_energy(self):
         b, ov, ok = C.c_longlong(0), C.c_int(0), C.c_int(0)

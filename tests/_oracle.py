@@ -68,6 +68,7 @@ def port_lib():
     L.ppo_total_bonds.restype = C.c_longlong
     L.ppo_total_bonds.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.ppo_bond_counts.argtypes = [C.c_void_p, _ip, _ip]
+    L.ppo_bond_lists.argtypes = [C.c_void_p, C.c_int, _ip, _ip]
     L.ppo_eval_proposals.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     L.ppo_volume_move.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
@@ -167,6 +168,12 @@ class PortSystem:
         self.L.ppo_bond_counts(self.h, c, o)
         return c[:self.N], o[:self.N]
 
+    def bond_lists(self, max_nb=8):
+        c = np.zeros(max(self.N, 1), dtype=np.int32)
+        nb = np.full((max(self.N, 1), max_nb), -1, dtype=np.int32)
+        self.L.ppo_bond_lists(self.h, max_nb, c, nb.reshape(-1))
+        return c[:self.N], nb[:self.N]
+
     def eval_proposals(self, idx, disp, orient_new, u, commit=False):
         n = len(idx)
         idx = np.ascontiguousarray(idx, dtype=np.int32)
@@ -197,6 +204,13 @@ class PortSystem:
         st = stats if stats is not None else SweepStats()
         self.L.ppo_sweep(self.h, seed, sweep_index, shift_every, disp_max, theta_max, C.byref(b), C.byref(st))
         return int(b.value), st
+
+
+def sorted_bond_lists(nb):
+    """Canonical form of a neighbour table for set comparison: every row ascending, the -1 padding last."""
+    a = np.where(nb < 0, np.iinfo(np.int32).max, nb)
+    a = np.sort(a, axis=1)
+    return np.where(a == np.iinfo(np.int32).max, -1, a).astype(np.int32)
 
 
 def rotate_port(m_old, axis, theta):
@@ -231,6 +245,7 @@ def ref_lib():
     L.ref_total_energy.restype = C.c_double
     L.ref_total_energy.argtypes = [C.POINTER(C.c_int)]
     L.ref_bond_counts.argtypes = [_ip, _ip]
+    L.ref_bond_lists.argtypes = [C.c_int, _ip, _ip]
     L.ref_rotate.argtypes = [_dp, _dp, C.c_double, _dp]
     L.ref_eval_proposals.argtypes = [C.c_int, _ip, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     L.ref_run_moves.argtypes = [C.c_long]
@@ -318,6 +333,13 @@ class RefSystem:
         o = np.zeros(self.N, dtype=np.int32)
         self.L.ref_bond_counts(c, o)
         return c, o
+
+    def bond_lists(self, max_nb=8):
+        """Bonded neighbours by the reference's MC_interact over all pairs (ascending index)."""
+        c = np.zeros(max(self.N, 1), dtype=np.int32)
+        nb = np.full((max(self.N, 1), max_nb), -1, dtype=np.int32)
+        self.L.ref_bond_lists(max_nb, c, nb.reshape(-1))
+        return c[:self.N], nb[:self.N]
 
     def rotate(self, m_old, axis, theta):
         out = np.zeros(9)

@@ -6,10 +6,12 @@ Bar: bit-exact integer bond counts, overlap flags, deltaE and accept/reject deci
 threshold tests, MC.c:232-266, 328-335); bit-exact positions; orientations within 4e-15 after
 sweeps (CUDA's sincos and glibc's sin/cos may differ in the last bit).
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import ROOT, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -116,6 +118,33 @@ def test_total_bonds_vs_port(pp, oracle, N, rho, delta, cosmax):
     e.upload(box, r, m)
     assert e.total_bonds() == port.total_bonds()
     assert np.array_equal(e.bond_counts(), port.bond_counts()[0])
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["fcc", "gen2000_rho0.5"])
+def test_bond_lists_golden(pp, oracle, name):
+    """pp_bond_lists (what output_print_bonds lists, output.c:213-268): the sets of bonded neighbours equal the golden
+    vectors (the reference's MC_interact over all pairs) and the restatement's; truncation keeps the counts."""
+    g = load_golden(name)
+    b = np.load(os.path.join(ROOT, "tests", "golden", "bond_lists.npz"))
+    delta, cosmax = b[f"{name}_params"]
+    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax)
+    e.upload(g["box"], g["r"], g["orient"])
+    counts, nb = e.bond_lists(12)
+    assert np.array_equal(counts, b[f"{name}_counts"])
+    assert np.array_equal(oracle.sorted_bond_lists(nb), b[f"{name}_neighbours"])
+    port = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax)
+    pc, pnb = port.bond_lists(12)
+    assert np.array_equal(counts, pc) and np.array_equal(oracle.sorted_bond_lists(nb), oracle.sorted_bond_lists(pnb))
+    c2, nb2 = e.bond_lists(2)  # more bonds than columns: the counts stay, the lists hold the first two
+    assert np.array_equal(c2, counts) and np.array_equal(nb2, nb[:, :2])
+    assert np.array_equal(e.bond_counts(), counts)
+    e.sweep(3)  # after moves (cell-sorted storage reshuffled): still consistent with a fresh count
+    counts, nb = e.bond_lists(12)
+    r, m = e.download()
+    port.set_state(r, m)
+    pc, pnb = port.bond_lists(12)
+    assert np.array_equal(counts, pc) and np.array_equal(oracle.sorted_bond_lists(nb), oracle.sorted_bond_lists(pnb))
     e.close()
 
 

@@ -101,6 +101,51 @@ def test_host_output_formats(tmp_path):
     assert p.returncode == 255 and "Mandatory key" in p.stderr
 
 
+def read_bonds_file(path):
+    lines = open(path).read().split("\n")
+    n = int(lines[0])
+    idx, counts, lists = [], [], []
+    for i in range(n):
+        a, b = lines[1 + 2 * i].split()
+        idx.append(int(a))
+        counts.append(int(b))
+        lists.append([int(x) for x in lines[2 + 2 * i].split()])
+    return n, np.array(idx), np.array(counts), lists
+
+
+def test_host_print_bonds(tmp_path):
+    """Print_bonds / Bonds_folder (output.c:88-99, 206-268): same file name, same layout, same counts as the reference
+    program for the common initial configuration; the neighbour line holds exactly the bonded neighbours (the
+    reference builds it with an overlapping sprintf, so its line is compared only where it parses to the same
+    number of entries); later files agree with the energy column."""
+    need_binaries()
+    d_ref, d_gpu = make_case(tmp_path, 1000, 0.4, Steps=40, Print_every=20, Print_bonds=1, Bonds_folder=".", KF_delta=0.25, KF_cosmax=0.8,
+                             Temperature=0.15)
+    run(REF_BIN, d_ref)
+    run(HOST_BIN, d_gpu)
+    for step in (0, 20):
+        assert (d_ref / f"bonds_{step}.dat").exists() and (d_gpu / f"bonds_{step}.dat").exists()
+    n_ref, i_ref, c_ref, l_ref = read_bonds_file(d_ref / "bonds_0.dat")
+    n_gpu, i_gpu, c_gpu, l_gpu = read_bonds_file(d_gpu / "bonds_0.dat")
+    assert n_ref == n_gpu == 1000 and np.array_equal(i_ref, i_gpu) and np.array_equal(c_ref, c_gpu)
+    assert c_gpu.sum() > 100  # the state point has bonds
+    assert all(len(l) == c for l, c in zip(l_gpu, c_gpu))
+    assert all(i in l_gpu[q] for i in range(1000) for q in l_gpu[i])  # mutual
+    comparable = [i for i in range(1000) if len(l_ref[i]) == c_ref[i]]
+    assert all(sorted(l_ref[i]) == sorted(l_gpu[i]) for i in comparable)
+    # later prints: the file is consistent with the running energy of the same step
+    e_gpu = load_cols(d_gpu / "energy.dat")
+    _, _, c20, l20 = read_bonds_file(d_gpu / "bonds_20.dat")
+    row = e_gpu[e_gpu[:, 0] == 20][0]
+    assert c20.sum() == round(-2 * row[1] * 1000)
+    # refused outside NVT, like the reference
+    write_input(d_gpu / "input", Dynamics=0, Ensemble=5, P=0.1, rescale_factor_max=0.01, Temperature=0.2, Steps=1, Disp_max=0.1,
+                Theta_max=0.1, Initial_conditions_file=str(tmp_path / "generated.rrr"), Print_every=1, Save_every=1,
+                Configuration_folder=".", KF_delta=0.119, KF_cosmax=0.92, Print_bonds=1, Bonds_folder=".")
+    p = subprocess.run([HOST_BIN, "input"], cwd=d_gpu, capture_output=True, text=True)
+    assert p.returncode == 1 and "non-canonical" in p.stderr
+
+
 def test_nvt_statistics_vs_reference(tmp_path):
     """<E>/N and roto-translation acceptance at equilibrium, N = 1000, rho = 0.4, T = 0.3, cosmax = 0.92."""
     need_binaries()

@@ -27,6 +27,24 @@ def test_port_total_bonds_golden(oracle, name):
         assert np.array_equal(p.cells(), g[f"ref_cells_{tag}"])
 
 
+@pytest.mark.parametrize("name", ["fcc", "gen2000_rho0.5"])
+def test_port_bond_lists_golden(oracle, name):
+    """Bonded-neighbour lists (output.c:213-268) of the restatement against the golden vectors, which are the
+    reference's own MC_interact over all pairs; live against the reference when it is built."""
+    g = load_golden(name)
+    b = np.load(os.path.join(ROOT, "tests", "golden", "bond_lists.npz"))
+    delta, cosmax = b[f"{name}_params"]
+    p = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax)
+    counts, nb = p.bond_lists(12)
+    assert np.array_equal(counts, b[f"{name}_counts"])
+    assert np.array_equal(oracle.sorted_bond_lists(nb), b[f"{name}_neighbours"])
+    assert np.array_equal((nb >= 0).sum(axis=1), counts)
+    # a bond is mutual
+    pairs = {(i, int(q)) for i in range(len(counts)) for q in nb[i] if q >= 0}
+    assert all((q, i) in pairs for i, q in pairs)
+    assert len(pairs) == 2 * p.total_bonds()[0]
+
+
 def test_known_answers_from_survey(oracle):
     """fcc.rrr -> -914 (343x4, 143x3, 13x2, 1x1); bcc.rrr -> 0 at delta 0.119, -92 at 0.135."""
     g = load_golden("fcc")

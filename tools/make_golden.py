@@ -66,8 +66,28 @@ def one(name, rrr, variants, n_prop=0, disp_max=0.3, theta_max=0.5, T=0.1, seed=
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
 
 
+def bond_lists():
+    """tests/golden/bond_lists.npz: bonded neighbours of every particle by the reference's MC_interact over all
+    pairs (what output_print_bonds, output.c:213-268, is meant to list), rows ascending, -1 padded."""
+    out = {}
+    tmp = "/tmp/_golden_gen.rrr"
+    O.run_generator(2000, 0.5, tmp)
+    for name, rrr, keys in (("fcc", os.path.join(REF, "fcc.rrr"), {"KF_cosmax": 0.92}),
+                            ("gen2000_rho0.5", tmp, {"KF_cosmax": 0.8, "KF_delta": 0.25})):
+        ref = O.RefSystem(rrr, Temperature=0.1, **keys)
+        counts, nb = ref.bond_lists(12)
+        assert counts.max() <= 12
+        out[f"{name}_counts"], out[f"{name}_neighbours"] = counts, O.sorted_bond_lists(nb)
+        out[f"{name}_params"] = np.array([keys.get("KF_delta", 0.119), keys.get("KF_cosmax", 0.98)])
+        print("bond lists", name, "bonds per particle", np.bincount(counts))
+        ref.close()
+    np.savez_compressed(os.path.join(GOLD, "bond_lists.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "bond_lists":
+        return bond_lists()
     one("fcc", os.path.join(REF, "fcc.rrr"), {"a": {}, "b": {"KF_cosmax": 0.92}}, n_prop=2048, T=0.11)
     one("bcc", os.path.join(REF, "bcc.rrr"), {"a": {}, "b": {"KF_delta": 0.135}}, n_prop=1024)
     tmp = "/tmp/_golden_gen.rrr"
@@ -77,6 +97,7 @@ def main():
     one("gen2000_rho0.5", tmp, {"a": {}, "b": {"KF_cosmax": 0.8, "KF_delta": 0.25}}, n_prop=4096)
     # known answers for the large generator outputs (configuration regenerated at test time by the
     # reference's deterministic generator when oracle/_ref/ is present)
+    bond_lists()
     known = {}
     for N, rho in [(32768, 0.3), (65536, 0.5)]:
         O.run_generator(N, rho, tmp)
