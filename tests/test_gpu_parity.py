@@ -202,6 +202,33 @@ def test_sweep_invariants_large(pp):
     e.close()
 
 
+def test_full_size_invariants(pp):
+    """BASELINE configs[3] size (N = 4 194 304, rho = 0.6) on one GPU, hybrid kernel routing: size-independent
+    properties -- attempt count, running energy == recount (MC_check_energy), no overlap, bond counts sum to twice
+    the bonds, orthonormal orientations, hard-core distances intact on a sample, download -> upload idempotence."""
+    N = 4194304
+    box, r, m = pp.random_fluid(N, 0.6, seed=3)
+    e = pp.Engine(temperature=0.1, seed=17)
+    e.upload(box, r, m)
+    b0, ov = e.total_bonds()
+    assert ov == 0
+    e.sweep(9)  # three grid shifts
+    o = e.observables()
+    assert o.tries[0] == 9 * N and 0 < o.accepted[0] < o.tries[0]
+    assert o.accepted[0] + o.confined + o.overlapped <= o.tries[0]
+    b, ov, ok = e.check_energy()
+    assert ok and ov == 0 and -o.energy == b
+    assert int(e.bond_counts().astype(np.int64).sum()) == 2 * b
+    r2, m2 = e.download()
+    assert np.abs(np.einsum("nij,nkj->nik", m2[::64], m2[::64]) - np.eye(3)).max() < 1e-12
+    assert 0 < np.abs(r2 - r).max() < 9 * 0.05 * 1.01
+    e2 = pp.Engine(temperature=0.1, seed=17)
+    e2.upload(box, r2, m2)
+    assert e2.total_bonds() == (b, 0)  # idempotent: the downloaded state re-counts to the same bonds, no overlap
+    e2.close()
+    e.close()
+
+
 def test_volume_move_vs_port(pp, oracle):
     g = load_golden("gen2000_rho0.5")
     delta, cosmax, T, P, rfm = 0.25, 0.8, 0.15, 0.5, 0.0005
