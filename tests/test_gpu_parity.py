@@ -202,6 +202,52 @@ def test_sweep_invariants_large(pp):
     e.close()
 
 
+@pytest.mark.parametrize("lanes,cell_lanes,cmo", [(0, 0, -1), (0, 1, 3), (0, 2, 1), (1, 1, -1), (1, 8, -1), (8, 0, -1)])
+def test_crystal_sweep_matches_port(pp, oracle, lanes, cell_lanes, cmo):
+    """BASELINE configs[4] in small: an FCC crystal at rho = 1.041 (dofccrrr.py recipe), 41-44 particles in a 27-cell
+    neighbourhood, up to 4 per cell.  Dense staging areas, crowded-cell routing and the serial fallback all follow the
+    CPU restatement bit for bit."""
+    box, r, m = pp.fcc_configuration(1.041, 6, 6, 6)
+    T = 1.0  # warm enough for ~1000 accepted moves in 8 sweeps, with displacements large enough for ~1000 overlaps
+    port = oracle.PortSystem(box, r, m, temperature=T)
+    e = pp.Engine(temperature=T, disp_max=0.15, theta_max=0.2, seed=5, lanes_per_cell=lanes, cell_lanes=cell_lanes, cells_max_occupancy=cmo)
+    e.upload(box, r, m)
+    pb, pov = port.total_bonds()
+    assert e.total_bonds() == (pb, pov) and pov == 0 and pb > 1000
+    st = oracle.SweepStats()
+    for s_ in range(8):
+        pb, st = port.sweep(5, s_, 0.15, 0.2, pb, st)
+    e.sweep(8)
+    assert st.accepted > 200 and st.overlapped > 200
+    o = e.observables()
+    assert -o.energy == pb and o.tries[0] == st.tries and o.accepted[0] == st.accepted
+    assert o.confined == st.confined and o.overlapped == st.overlapped and o.pair_checks == st.pair_checks
+    rr, mm = e.download()
+    pr, pm = port.state()
+    assert np.array_equal(rr, pr) and np.abs(mm - pm).max() < 4e-15
+    e.close()
+
+
+def test_crystal_melt_invariants(pp):
+    """BASELINE configs[4] at full size: FCC 40 x 40 x 40 x 4 = 256 000 particles, rho = 1.041, T = 0.11, with the
+    automatic kernel choice and with the hybrid routing forced."""
+    box, r, m = pp.fcc_configuration(1.041, 40, 40, 40)
+    results = []
+    for cmo in (-1, 3):
+        e = pp.Engine(temperature=0.11, seed=9, cells_max_occupancy=cmo)
+        e.upload(box, r, m)
+        b0, ov = e.total_bonds()
+        assert ov == 0 and b0 > 400000  # nearly four bonds per particle in the perfect crystal
+        e.sweep(12)
+        o = e.observables()
+        b, ov, ok = e.check_energy()
+        assert ok and ov == 0 and -o.energy == b and o.tries[0] == 12 * 256000
+        results.append((b, o.accepted[0], o.confined, o.overlapped, e.download()[0]))
+        e.close()
+    # the kernel choice does not change the trajectory
+    assert results[0][:4] == results[1][:4] and np.array_equal(results[0][4], results[1][4])
+
+
 def test_full_size_invariants(pp):
     """BASELINE configs[3] size (N = 4 194 304, rho = 0.6) on one GPU, hybrid kernel routing: size-independent
     properties -- attempt count, running energy == recount (MC_check_energy), no overlap, bond counts sum to twice
