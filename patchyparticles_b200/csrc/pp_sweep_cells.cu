@@ -1,13 +1,18 @@
-// pp_sweep_cells.cu -- K2b, one THREAD per non-empty cell of the current colour.
+// pp_sweep_cells.cu -- K2b, G lanes (1, 2, 4 or 8) per non-empty cell of the current colour.
 //
 // Same algorithm, same random streams and bit-identical trajectories as the tile kernel in
 // pp_sweep.cu (both are checked against the serial restatement in oracle/pp_oracle.c); what changes
-// is the mapping onto the machine.  A thread walks its cell's trials on its own, so nothing is
-// computed redundantly, shuffled or reduced: ~3-4x fewer warp instructions per trial than the tile
-// kernel.  The price is a serial chain per cell, so the engine routes only sparsely populated cells
-// here (at most kCellsMaxOccupancy members: >95 % of the cells of a fluid) and the crowded ones to
-// the tile kernel, both running concurrently on two streams.  The work list hands consecutive
-// threads cells of equal occupancy, which keeps the lanes of a warp in the same trial.
+// is the mapping onto the machine and the arithmetic of the screens.
+//   G = 1  a thread walks its cell's trials on its own, so nothing is computed redundantly, shuffled or
+//          reduced: about half the warp instructions per trial of the tile kernel.  The price is a serial
+//          chain per cell, so the cell build routes the sparsely populated cells here (at most M members,
+//          at most kCellsNbCap staged neighbours: >95 % of the cells of a fluid) ...
+//   G = 8  ... and the crowded ones to the 8-lane configuration, whose lanes split the nine columns of the
+//          neighbourhood and which also stages the cell's proposals and the FP64 state of its own particles
+//          (shortest chain per trial).  The two launches of a colour pass run concurrently on two streams.
+// The work list hands consecutive groups cells of equal occupancy, which keeps the lanes of a warp in the same
+// trial.  No TMA: the staging is a gather of 8-byte items from ~27 short runs per cell, not a tile; cp.async
+// (LDGSTS) is the fire-and-forget primitive that fits it.
 //
 //   per cell   the shadow positions (8 bytes: 16-bit fixed-point offset inside the cell + rank in the
 //              cell) of the 27-cell neighbourhood are brought into shared memory with cp.async -- all
