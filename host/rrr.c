@@ -37,9 +37,53 @@ static void build_orientation(const double *a, const double *b, double *m) {
 	unit(v3);
 }
 
+static const char kRrbMagic[8] = {'P', 'P', 'R', 'R', 'B', '1', 0, 0};
+
+static int rrb_read(FILE *f, long long *step, int *N, double box[3], double **r_out, double **m_out, int *found) {
+	long long head[2];
+	if(fread(head, sizeof(long long), 2, f) != 2 || fread(box, sizeof(double), 3, f) != 3 || head[1] < 0 || head[1] > 2147483647LL) return -2;
+	const size_t n = (size_t) head[1], cap = n > 0 ? n : 1;
+	double *r = malloc(cap * 3 * sizeof(double)), *m = malloc(cap * 9 * sizeof(double));
+	if(r == NULL || m == NULL) {
+		free(r);
+		free(m);
+		return -2;
+	}
+	const size_t got_r = fread(r, 3 * sizeof(double), n, f), got_m = fread(m, 9 * sizeof(double), n, f);
+	if(found) *found = (int) (got_m < got_r ? got_m : got_r);
+	if(got_r != n || got_m != n) {
+		free(r);
+		free(m);
+		return -3;
+	}
+	if(step) *step = head[0];
+	*N = (int) n;
+	*r_out = r;
+	*m_out = m;
+	return 0;
+}
+
+int pph_rrb_write(const char *path, long long step, int N, const double box[3], const double *r, const double *m) {
+	FILE *f = fopen(path, "wb");
+	if(f == NULL) return -1;
+	const long long head[2] = {step, N};
+	int ok = fwrite(kRrbMagic, 1, 8, f) == 8 && fwrite(head, sizeof(long long), 2, f) == 2 && fwrite(box, sizeof(double), 3, f) == 3;
+	ok = ok && fwrite(r, 3 * sizeof(double), (size_t) N, f) == (size_t) N && fwrite(m, 9 * sizeof(double), (size_t) N, f) == (size_t) N;
+	return (fclose(f) == 0 && ok) ? 0 : -1;
+}
+
 int pph_rrr_read(const char *path, long long *step, int *N, double box[3], double **r_out, double **m_out, int *found) {
 	FILE *f = fopen(path, "r");
 	if(f == NULL) return -1;
+	{ /* binary side format? */
+		char magic[8];
+		if(fread(magic, 1, 8, f) == 8 && memcmp(magic, kRrbMagic, 8) == 0) {
+			const int rc = rrb_read(f, step, N, box, r_out, m_out, found);
+			fclose(f);
+			return rc;
+		}
+		rewind(f);
+	}
 	long long st;
 	int n;
 	if(fscanf(f, "%lld %d %lf %lf %lf", &st, &n, box, box + 1, box + 2) != 5 || n < 0) {

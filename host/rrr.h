@@ -12,4 +12,10 @@ int pph_rrr_read(const char *path, long long *step, int *N, double box[3], doubl
  * ("%.12lf %.12lf %.12lf").  Returns 0 on success. */
 int pph_rrr_write(const char *path, long long step, int N, const double box[3], const double *r, const double *orient);
 
+/* Binary side format for large systems (the text format costs ~0.5 GB and minutes of fscanf at N = 4M,
+ * and rounds positions to 1e-12 and orientations to 1e-6).  Little endian: 8 bytes "PPRRB1\0\0", int64 step,
+ * int64 N, double box[3], N x 3 doubles positions, N x 9 doubles orientation matrices (row major, used as stored).
+ * pph_rrr_read recognises it by the magic bytes. */
+int pph_rrb_write(const char *path, long long step, int N, const double box[3], const double *r, const double *orient);
+
 #endif

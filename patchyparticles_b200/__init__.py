@@ -6,8 +6,8 @@ mirror of that ABI used by the tests and by ``bench.py``.  There is no CPU fallb
 :class:`Engine` without the built library, or creating one without a CUDA device, raises.
 """
 from .engine import Engine, Params, Observables, load_library, library_path, LibraryMissing  # noqa: F401
-from .rrr import read_rrr, write_rrr, orientation_from_rows  # noqa: F401
+from .rrr import read_rrr, write_rrr, read_rrb, write_rrb, orientation_from_rows  # noqa: F401
 from .configs import fcc_configuration, random_fluid  # noqa: F401
 
 __all__ = ["Engine", "Params", "Observables", "load_library", "library_path", "LibraryMissing",
-           "read_rrr", "write_rrr", "orientation_from_rows", "fcc_configuration", "random_fluid"]
+           "read_rrr", "write_rrr", "read_rrb", "write_rrb", "orientation_from_rows", "fcc_configuration", "random_fluid"]

@@ -27,8 +27,40 @@ def orientation_from_rows(row0, row1):
     return np.stack([_normalize(v1), _normalize(v2), _normalize(v3)], axis=-2)
 
 
+RRB_MAGIC = b"PPRRB1\0\0"
+
+
+def read_rrb(path):
+    """Binary side format (host/rrr.h): magic, int64 step, int64 N, box[3], N x 3 positions, N x 9 orientation
+    matrices, all little endian, full FP64.  -> (step, box[3], r[N,3], orient[N,3,3])"""
+    with open(path, "rb") as f:
+        if f.read(8) != RRB_MAGIC:
+            raise ValueError(f"{path}: not a .rrb file")
+        step, n = (int(x) for x in np.frombuffer(f.read(16), dtype="<i8"))
+        box = np.frombuffer(f.read(24), dtype="<f8").copy()
+        r = np.frombuffer(f.read(24 * n), dtype="<f8")
+        m = np.frombuffer(f.read(72 * n), dtype="<f8")
+    if r.size != 3 * n or m.size != 9 * n:
+        raise ValueError(f"Number of particles found in configuration is different from the value found in the header ({n})")
+    return step, box, r.reshape(n, 3).copy(), m.reshape(n, 3, 3).copy()
+
+
+def write_rrb(path, step, box, r, orient):
+    r = np.ascontiguousarray(r, dtype="<f8").reshape(-1, 3)
+    orient = np.ascontiguousarray(orient, dtype="<f8").reshape(-1, 9)
+    with open(path, "wb") as f:
+        f.write(RRB_MAGIC)
+        f.write(np.array([step, len(r)], dtype="<i8").tobytes())
+        f.write(np.ascontiguousarray(box, dtype="<f8").tobytes())
+        f.write(r.tobytes())
+        f.write(orient.tobytes())
+
+
 def read_rrr(path):
-    """-> (step, box[3], r[N,3], orient[N,3,3])"""
+    """-> (step, box[3], r[N,3], orient[N,3,3]); the binary side format is recognised by its magic bytes"""
+    with open(path, "rb") as f:
+        if f.read(8) == RRB_MAGIC:
+            return read_rrb(path)
     with open(path) as f:
         head = f.readline().split()
         step, n = int(head[0]), int(head[1])

@@ -146,6 +146,35 @@ def test_host_print_bonds(tmp_path):
     assert p.returncode == 1 and "non-canonical" in p.stderr
 
 
+def test_generator_melt_and_binary_input(tmp_path):
+    """patchy_generate with a GPU melt and the binary side format as Initial_conditions_file."""
+    need_binaries()
+    gen = os.path.join(ROOT, "host", "patchy_generate")
+    if not os.path.exists(gen):
+        pytest.skip("host/patchy_generate not built")
+    import patchyparticles_b200 as pkg
+    subprocess.run([gen, "20000", "0.5", "3", "lattice.rrb"], cwd=tmp_path, check=True, capture_output=True)
+    p = subprocess.run([gen, "20000", "0.5", "3", "melted.rrb", "60"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 0 and "Melted for 60 sweeps" in p.stderr, p.stderr[-1000:]
+    _, box, r0, m0 = pkg.read_rrr(str(tmp_path / "lattice.rrb"))
+    _, box1, r1, m1 = pkg.read_rrr(str(tmp_path / "melted.rrb"))
+    assert np.array_equal(box, box1) and len(r1) == 20000
+    assert np.abs(r1 - r0).mean() > 0.2  # the particles left their lattice sites
+    e = pkg.Engine()
+    e.upload(box1, r1, m1)
+    assert e.total_bonds()[1] == 0  # no overlap
+    e.close()
+    # the C host starts from the binary file
+    d = tmp_path / "run"
+    d.mkdir()
+    write_input(d / "input", Dynamics=0, Ensemble=0, Temperature=0.2, Steps=10, Disp_max=0.1, Theta_max=0.1,
+                Initial_conditions_file=str(tmp_path / "melted.rrb"), Print_every=5, Save_every=100, Configuration_folder=".",
+                KF_delta=0.119, KF_cosmax=0.92, Seed=1, Log_file="none")
+    run(HOST_BIN, d)
+    step, box2, r2, _ = pkg.read_rrr(str(d / "last.rrr"))
+    assert step == 10 and len(r2) == 20000 and np.allclose(box2, box1)
+
+
 def test_nvt_statistics_vs_reference(tmp_path):
     """<E>/N and roto-translation acceptance at equilibrium, N = 1000, rho = 0.4, T = 0.3, cosmax = 0.92."""
     need_binaries()

@@ -45,6 +45,49 @@ def test_port_bond_lists_golden(oracle, name):
     assert len(pairs) == 2 * p.total_bonds()[0]
 
 
+GEN_BIN = os.path.join(ROOT, "host", "patchy_generate")
+
+
+def test_generator_at_scale(oracle, tmp_path):
+    """host/patchy_generate: the files load like the reference generator's (generator.c:73-81
+    layout), hold N non-overlapping spheres at the requested density, are reproducible per seed, and the binary
+    side format round-trips bit for bit.  The reference itself accepts them (no overlap, same energy)."""
+    import subprocess
+    import patchyparticles_b200 as pkg
+    if not os.path.exists(GEN_BIN):
+        pytest.skip("host/patchy_generate not built")
+    run = lambda *a: subprocess.run([GEN_BIN, *[str(x) for x in a]], cwd=tmp_path, check=True, capture_output=True)
+    run(3000, 0.6, 7, "a.rrr")
+    run(3000, 0.6, 7, "b.rrr")
+    run(3000, 0.6, 8, "c.rrr")
+    run(3000, 0.6, 7, "a.rrb")
+    assert open(tmp_path / "a.rrr").read() == open(tmp_path / "b.rrr").read() != open(tmp_path / "c.rrr").read()
+    step, box, r, m = pkg.read_rrr(str(tmp_path / "a.rrr"))
+    assert step == 0 and len(r) == 3000 and np.allclose(box, (3000 / 0.6) ** (1 / 3), rtol=0, atol=1e-11)
+    assert r.min() >= 0 and r.max() <= box[0]
+    assert np.abs(np.einsum("nij,nkj->nik", m, m) - np.eye(3)).max() < 1e-12
+    port = oracle.PortSystem(box, r, m, kf_delta=0.25, kf_cosmax=0.8)
+    bonds, overlap = port.total_bonds()
+    assert overlap == 0 and bonds > 0  # random orientations at rho = 0.6: a few bonds
+    # binary twin: same state at full precision (the text file rounds positions to 1e-12, rows to 1e-6)
+    sb, bb, rb, mb = pkg.read_rrr(str(tmp_path / "a.rrb"))
+    assert sb == 0 and np.abs(bb - box).max() < 1e-11 and np.abs(rb - r).max() < 1e-11 and np.abs(mb - m).max() < 2e-6
+    pkg.write_rrb(str(tmp_path / "again.rrb"), 5, bb, rb, mb)
+    s2, b2, r2, m2 = pkg.read_rrb(str(tmp_path / "again.rrb"))
+    assert s2 == 5 and np.array_equal(b2, bb) and np.array_equal(r2, rb) and np.array_equal(m2, mb)
+    # densities the reference generator refuses (generator.c:99-102) still work, impossible ones are refused
+    run(4000, 0.9, 1, "dense.rrr")
+    _, box_d, r_d, m_d = pkg.read_rrr(str(tmp_path / "dense.rrr"))
+    assert oracle.PortSystem(box_d, r_d, m_d).total_bonds()[1] == 0
+    p = subprocess.run([GEN_BIN, "4000", "1.2"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and "cannot produce" in p.stderr
+    if oracle.have_ref():
+        ref = oracle.RefSystem(str(tmp_path / "a.rrr"), Temperature=0.1, KF_delta=0.25, KF_cosmax=0.8)
+        e, ov = ref.total_energy()
+        assert ov == 0 and -e == bonds
+        ref.close()
+
+
 def test_known_answers_from_survey(oracle):
     """fcc.rrr -> -914 (343x4, 143x3, 13x2, 1x1); bcc.rrr -> 0 at delta 0.119, -92 at 0.135."""
     g = load_golden("fcc")
