@@ -248,6 +248,39 @@ def test_crystal_melt_invariants(pp):
     assert results[0][:4] == results[1][:4] and np.array_equal(results[0][4], results[1][4])
 
 
+def test_npt_and_lx_full_size_invariants(pp):
+    """BASELINE configs[2] size (N = 32768, rho = 0.3): NPT sweeps with volume moves (Ensemble = 5, P = 0.5, T = 0.15)
+    and NVT sweeps with Lx moves keep the invariants -- volume-move attempts are Binomial(N, 1/N) per step as in
+    MC.c:60-68, the box volume moves (NPT) or is conserved with Ly = Lz (Lx), running energy == recount, no overlap."""
+    N = 32768
+    box, r, m = pp.random_fluid(N, 0.3, seed=5)
+    e = pp.Engine(ensemble=5, temperature=0.15, P=0.5, rescale_factor_max=1e-3, seed=3)
+    e.upload(box, r, m)
+    e.total_bonds()
+    e.sweep(60)
+    o = e.observables()
+    assert o.tries[0] == 60 * N                        # a sweep is N roto-translation attempts ...
+    assert 20 <= o.tries[6] <= 120 and o.accepted[6] <= o.tries[6]  # ... plus Binomial(N, 1/N) volume moves per step
+    V0, V1 = float(np.prod(box)), float(np.prod(o.box))
+    assert (V1 != V0) == (o.accepted[6] > 0) and abs(V1 / V0 - 1) < 0.05
+    b, ov, ok = e.check_energy()
+    assert ok and ov == 0 and -o.energy == b
+    r2, _ = e.download()
+    assert np.isfinite(r2).all()
+    e.close()
+    L = float(box[0])
+    e = pp.Engine(temperature=0.15, Lx_move=1, Lx_change_max=0.01, Lyz_min=20., Lyz_max=80., seed=4)
+    e.upload(box, r, m)
+    e.total_bonds()
+    e.sweep(60)
+    o = e.observables()
+    assert o.tries[0] == 60 * N and 20 <= o.tries[7] <= 120
+    assert abs(float(np.prod(o.box)) / L ** 3 - 1) < 1e-12 and o.box[1] == o.box[2]  # MC.c:521-524: V fixed, Ly = Lz
+    b, ov, ok = e.check_energy()
+    assert ok and ov == 0 and -o.energy == b
+    e.close()
+
+
 def test_full_size_invariants(pp):
     """BASELINE configs[3] size (N = 4 194 304, rho = 0.6) on one GPU, hybrid kernel routing: size-independent
     properties -- attempt count, running energy == recount (MC_check_energy), no overlap, bond counts sum to twice
