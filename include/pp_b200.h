@@ -64,7 +64,7 @@ typedef struct pp_params {
 	                               4, 8, 16, 32 = tile kernel of that width (for the crowded cells if cells_max_occupancy > 0) */
 	int cell_lanes;             /* lanes per cell of the thread-per-cell kernel for the sparsely populated cells: 0 = 1, or 1, 2, 4, 8 */
 	int cells_max_occupancy;    /* hybrid routing: cells with at most this many particles go to the thread-per-cell kernel;
-	                               -1 = automatic (3 for N >= 800k, 2 for N >= 300k, else 0), 0 = tile kernel only */
+	                               -1 = automatic (3 for N >= 800k, 2 for N >= 400k, 1 for N >= 150k, else 0), 0 = tile kernel only */
 	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
 } pp_params;
 

@@ -329,7 +329,7 @@ int cells_occupancy_limit(const pp_handle *h) {
 	if(h->prm.lanes_per_cell != 0) return 0; // an explicit tile width alone: tile kernel only
 	// measured on B200 (profiles/README.md): the thread-per-cell kernel wins once a colour pass fills the GPU; the
 	// smaller the pass, the more its serial chain per cell matters and the fewer particles a cell may hold there
-	return (h->N >= 800000) ? 3 : ((h->N >= 300000) ? 2 : 0);
+	return (h->N >= 800000) ? 3 : ((h->N >= 400000) ? 2 : ((h->N >= 150000) ? 1 : 0));
 }
 
 // lanes per cell of the thread-per-cell kernel: one lane per cell has the highest throughput, more lanes shorten
