@@ -60,6 +60,10 @@ class _DeviceBuffer:
 def device_view(ptr, n, dtype, device):
     if n == 0:
         return torch.empty(0, dtype=dtype, device=device)
+    if device.type == "cpu":  # stand-in engines of the CPU tests hand out host pointers
+        import ctypes
+        itemsize = {torch.float64: 8, torch.float32: 4, torch.int32: 4}[dtype]
+        return torch.frombuffer((ctypes.c_char * (n * itemsize)).from_address(ptr), dtype=dtype)
     typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4"}[dtype]
     return torch.as_tensor(_DeviceBuffer(ptr, n, typestr), device=device)
 
@@ -100,18 +104,24 @@ def exchange_counts(rank, world, n_to_left, n_to_right, device, group=None):
 class SlabEngine:
     """One rank of a slab-decomposed simulation.  Mirrors :class:`Engine` for the NVT path."""
 
-    def __init__(self, rank, world, device_index, **params):
+    def __init__(self, rank, world, device_index, engine=None, transport=None, **params):
+        """``engine`` / ``transport`` are for the CPU tests of this driver: a stand-in engine object (tensors then live
+        on the CPU) and "peer" / "nccl" instead of the PP_SLAB_HALO environment variable."""
         if world < 2:
             raise ValueError("SlabEngine needs at least two ranks; use Engine on one GPU")
         self.rank, self.world = rank, world
-        self.device = torch.device("cuda", device_index)
-        self.eng = Engine(device=device_index, **params)
-        self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        if engine is None:
+            self.device = torch.device("cuda", device_index)
+            self.eng = Engine(device=device_index, **params)
+            self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        else:
+            self.device = torch.device("cpu")
+            self.eng = engine
         self.eng.slab_setup(rank, world)
         self.N = 0
         self._halo_cache = [None, None]
         self._rebuilds = 0
-        self.peer_halo = HALO_TRANSPORT == "peer"
+        self.peer_halo = (transport or HALO_TRANSPORT) == "peer"
 
     def close(self):
         if self.peer_halo:
