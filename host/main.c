@@ -120,7 +120,7 @@ static void print_bonds(host_output *out, pp_handle *h, int N, llint step) {
 static void print_observables(host_output *out, pp_handle *h, const pp_params *prm, llint step) {
 	pp_observables o;
 	PP_CALL(out, h, pp_get_observables(h, &o, 1)); /* counters are reset after each print (output.c:189) */
-	const double V = o.box[0] * o.box[1] * o.box[2];
+	const double V = o.volume; /* System.V, output.c:131 */
 	const double E = (o.N > 0) ? o.energy / o.N : 0.;
 	fprintf(out->energy, "%lld %lf\n", step, E);
 	fflush(out->energy);
@@ -320,7 +320,7 @@ int main(int argc, char *argv[]) {
 		pp_observables o;
 		PP_CALL(&out, h, pp_get_observables(h, &o, 0));
 		printf("%lld %lf %lf", step, (o.N > 0) ? o.energy / o.N : 0., o.energy);
-		if(prm.ensemble != PP_NVT) printf(" %lf", o.N / (o.box[0] * o.box[1] * o.box[2]));
+		if(prm.ensemble != PP_NVT) printf(" %lf", o.N / o.volume);
 		printf("\n");
 	}
 

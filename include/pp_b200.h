@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 
 /* move-type slots of System.tries[] / accepted[] (defs.h:11-19) */
 #define PP_N_MOVES 8
@@ -81,6 +81,7 @@ typedef struct pp_observables {
 	double acceptance_roto;              /* estimator of the reference's accepted/tries for ROTO_TRASL */
 	long long pair_checks;               /* pair tests executed by the sweep kernel */
 	int n_side[3];                       /* current (even) cell grid */
+	double volume;                       /* System.V (system.c:198, MC.c:500): what density.dat divides by, output.c:131 */
 } pp_observables;
 
 void pp_default_params(pp_params *p);

@@ -21,6 +21,7 @@
 struct ppo_system {
 	int N;
 	double box[3];
+	double V;        /* System.V: set from the box at start-up (system.c:198), replaced by an accepted volume move (MC.c:500) */
 	double T;
 	double kf_delta, kf_cosmax, sqr_rcut, r_cut;
 	double base[12];
@@ -216,6 +217,7 @@ ppo_system *ppo_create(int N, const double *box, const double *r, const double *
 	ppo_system *s = calloc(1, sizeof(ppo_system));
 	s->N = N;
 	memcpy(s->box, box, 3 * sizeof(double));
+	s->V = box[0] * box[1] * box[2];
 	s->T = temperature;
 	s->kf_delta = kf_delta;
 	s->kf_cosmax = kf_cosmax;
@@ -255,7 +257,10 @@ void ppo_get_state(const ppo_system *s, double *r, double *orient) {
 
 void ppo_set_state(ppo_system *s, const double *r, const double *orient, const double *box) {
 	int i;
-	if(box != NULL) memcpy(s->box, box, 3 * sizeof(double));
+	if(box != NULL) {
+		memcpy(s->box, box, 3 * sizeof(double));
+		s->V = box[0] * box[1] * box[2];
+	}
 	memcpy(s->r, r, (size_t) s->N * 3 * sizeof(double));
 	memcpy(s->m, orient, (size_t) s->N * 9 * sizeof(double));
 	for(i = 0; i < s->N; i++) patches_from(s->base, s->m + 9 * i, s->patches + 12 * i);
@@ -406,6 +411,7 @@ int ppo_volume_move(ppo_system *s, double P, double rescale_factor_max, double u
 	double arg = -(P * delta_V + delta_E) / s->T + (s->N + 1) * log(f);
 	*overlap_out = ov;
 	if(!ov && u_acc < exp(arg)) {
+		s->V = final_V; /* MC.c:500 */
 		*energy_bonds = bonds_new;
 		return 1;
 	}
@@ -419,10 +425,9 @@ int ppo_Lx_move(ppo_system *s, double Lx_change_max, double Lyz_min, double Lyz_
 	/* MC.c:515-585.  faithful_sign != 0 reproduces the reference's exp(+dE/T) test (MC.c:562). */
 	int i, k;
 	double old[3] = {s->box[0], s->box[1], s->box[2]};
-	double V = old[0] * old[1] * old[2];
 	*overlap_out = 0;
 	s->box[0] += (u_lx - 0.5) * Lx_change_max;
-	s->box[1] = s->box[2] = sqrt(V / s->box[0]);
+	s->box[1] = s->box[2] = sqrt(s->V / s->box[0]); /* MC.c:524: the stored volume, not the product of the current sides */
 	if(s->box[1] < Lyz_min || s->box[1] > Lyz_max) {
 		memcpy(s->box, old, sizeof(old));
 		return -1;
@@ -657,7 +662,9 @@ void ppo_sweep(ppo_system *s, uint64_t seed, uint64_t sweep, int shift_every, do
 							st->confined++;
 							continue;
 						}
-						double W = 1. / ((1. - fabs(disp[0]) * inv_w[0]) * (1. - fabs(disp[1]) * inv_w[1]) * (1. - fabs(disp[2]) * inv_w[2]));
+						double keep = (1. - fabs(disp[0]) * inv_w[0]) * (1. - fabs(disp[1]) * inv_w[1]) * (1. - fabs(disp[2]) * inv_w[2]);
+						if(keep < 0.0078125) keep = 0.0078125; /* Disp_max comparable to the cell: the 2^-24 fixed point must not wrap */
+						double W = 1. / keep;
 						uint64_t Wfix = (uint64_t) (W * 16777216.0);
 						st->w_tries += Wfix;
 

@@ -233,3 +233,17 @@ void ref_run_steps(long n) {
 void ref_check_energy(void) { MC_check_energy(&g_syst, &g_out); }
 void ref_volume_move(void) { MC_change_volume(&g_syst, &g_out); }
 void ref_Lx_move(void) { MC_change_Lx(&g_syst, &g_out); }
+
+/* the reference's own helpers, driven directly (utils.c:115-131 draws from the drand48 above; utils.c:91-113) */
+void ref_random_vector_on_sphere(double *out) {
+	vector v;
+	random_vector_on_sphere(v);
+	memcpy(out, v, sizeof(vector));
+}
+
+void ref_gram_schmidt(double *m) {
+	gram_schmidt(m, m + 3, m + 6);
+}
+
+/* per-move bookkeeping the tests read after ref_volume_move / ref_Lx_move */
+double ref_volume(void) { return g_syst.V; }

@@ -56,6 +56,7 @@ struct pp_handle {
 	size_t cap_N;
 	size_t cap_cells;
 	double box[3];
+	double V;      // System.V: box product at upload (system.c:198), replaced by an accepted volume move (MC.c:500)
 	double r_cut;
 	double base[12];
 
@@ -79,6 +80,7 @@ struct pp_handle {
 	double shift[3];
 	bool cells_valid;
 	bool sweep_grid; // the current cells were built for the current sweep period's shift
+	int occ_limit;   // the routing threshold the current work lists were split with (cells_occupancy_limit at build time)
 
 	// bookkeeping
 	long long step;
@@ -86,6 +88,7 @@ struct pp_handle {
 	bool bonds_known;
 	long long tries[PP_N_MOVES], accepted[PP_N_MOVES];
 	uint64_t box_draws;
+	long long small_box_rejections; // box moves refused because the trial box could not hold two cells per side
 
 	// x-slab decomposition (one engine per GPU; world == 1: the whole periodic box)
 	int slab_rank, slab_world;
@@ -348,7 +351,7 @@ int tile_lanes(const pp_handle *h) {
 
 // the colour passes `first_pass .. first_pass + n_pass - 1` of one sweep (pass order: x parity slowest)
 int launch_passes(pp_handle *h, const SimConst &sc, int first_pass, int n_pass) {
-	const int limit = cells_occupancy_limit(h), lanes = tile_lanes(h);
+	const int limit = h->occ_limit, lanes = tile_lanes(h); // the split the work lists were built with, not a fresh evaluation
 	long long n_active = (long long) (sc.nxl / 2 + 1) * (sc.n_side[1] / 2) * (sc.n_side[2] / 2);
 	if(n_active > sc.N) n_active = sc.N;
 	int nl = 0;
@@ -402,7 +405,8 @@ int rebin(pp_handle *h, const double *shift) {
 	const SimConst sc = make_const(h, h->box, h->shift);
 	const int np = (h->cp + 1) % 3, no = h->co ^ 1;
 	prof_begin(h);
-	const int nl = launch_cell_build(sc, h->cb, view(h, h->cp, h->co), view(h, np, no), h->slot_of, cells_occupancy_limit(h), h->stream);
+	h->occ_limit = cells_occupancy_limit(h);
+	const int nl = launch_cell_build(sc, h->cb, view(h, h->cp, h->co), view(h, np, no), h->slot_of, h->occ_limit, h->stream);
 	prof_end(h, PP_K_CELLS, nl);
 	h->cp = np;
 	h->co = no;
@@ -467,6 +471,17 @@ int binomial_one_over_N(pp_handle *h) {
 	return k;
 }
 
+// A trial box with a side below two cells of side r_cut cannot carry the checkerboard grid.  The reference clamps its
+// grid to three cells per side there (cells.c:24-27) and evaluates the move with cells smaller than the interaction
+// range; the engine counts the move as tried and rejected and leaves positions, box and cells untouched, so a
+// compressing run goes on instead of aborting.
+bool box_too_small(pp_handle *h, const double *nb) {
+	int ns[3];
+	if(even_grid(nb, h->r_cut, ns) == 0) return false;
+	h->small_box_rejections++;
+	return true;
+}
+
 // One box move: rescale into the trial buffer, recount, Metropolis on the host.
 // factors f[3], new box nb[3]; arg_fn computes the acceptance exponent from (bonds_new).
 int box_trial(pp_handle *h, const double *nb, const double *f, long long *bonds_new, int *overlap) {
@@ -515,6 +530,10 @@ int volume_move(pp_handle *h, double u_dir, double u_vol, double u_acc, int *acc
 	f[dir] = rescale;
 	double old_box[3] = {h->box[0], h->box[1], h->box[2]};
 
+	if(box_too_small(h, nb)) { // counted, rejected, nothing touched
+		*accepted = 0;
+		return 0;
+	}
 	long long bonds_new = 0;
 	int overlap = 0;
 	int rc = box_trial(h, nb, f, &bonds_new, &overlap);
@@ -535,6 +554,7 @@ int volume_move(pp_handle *h, double u_dir, double u_vol, double u_acc, int *acc
 			memcpy(h->box, nb, sizeof(h->box));
 			for(int k = 0; k < 3; k++) h->shift[k] *= f[k];
 		}
+		h->V = final_V; // MC.c:500
 		h->bonds_base = bonds_new - h->h_counters->dbonds;
 		h->accepted[PP_VOLUME]++;
 		h->sweep_grid = false;
@@ -558,16 +578,19 @@ int Lx_move(pp_handle *h, double u_lx, double u_acc, int *accepted) {
 	// MC.c:515-585
 	if(fetch_counters(h)) return 1;
 	h->tries[PP_LX]++;
-	const double V = h->box[0] * h->box[1] * h->box[2];
 	double old_box[3] = {h->box[0], h->box[1], h->box[2]};
 	double nb[3];
 	nb[0] = h->box[0] + (u_lx - 0.5) * h->prm.Lx_change_max;
-	nb[1] = nb[2] = sqrt(V / nb[0]);
+	nb[1] = nb[2] = sqrt(h->V / nb[0]); // MC.c:524: the stored volume, not the product of the current sides
 	if(nb[1] < h->prm.Lyz_min || nb[1] > h->prm.Lyz_max) {
 		*accepted = -1;
 		return 0;
 	}
 	double f[3] = {nb[0] / old_box[0], nb[1] / old_box[1], nb[2] / old_box[2]};
+	if(box_too_small(h, nb)) { // counted, rejected, nothing touched
+		*accepted = 0;
+		return 0;
+	}
 	long long bonds_new = 0;
 	int overlap = 0;
 	int rc = box_trial(h, nb, f, &bonds_new, &overlap);
@@ -735,6 +758,7 @@ int pp_upload(pp_handle *h, int N, const double *box, const double *r, const dou
 	h->N = N;
 	h->N_global = N;
 	memcpy(h->box, box, sizeof(h->box));
+	h->V = box[0] * box[1] * box[2];
 	if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", box[0], box[1], box[2], h->r_cut);
 	h->nxl = h->n_side[0];
 	if(h->slab_world > 1) {
@@ -914,6 +938,7 @@ int pp_get_observables(pp_handle *h, pp_observables *obs, int reset) {
 	obs->acceptance_roto = (c.w_tries > 0) ? (double) c.w_accepted / (double) c.w_tries : NAN;
 	obs->pair_checks = c.pair_checks;
 	memcpy(obs->n_side, h->n_side, sizeof(obs->n_side));
+	obs->volume = h->V;
 	if(reset) {
 		// keep the energy: fold dbonds into the base, zero everything else (output.c:189)
 		h->bonds_base += c.dbonds;
@@ -1130,7 +1155,8 @@ int pp_slab_sweep_rebuild(pp_handle *h) {
 	memcpy(h->shift, h->pending_shift, sizeof(h->shift));
 	const SimConst sc = make_const(h, h->box, h->shift);
 	prof_begin(h);
-	const int nl = launch_cell_build(sc, h->cb, view(h, tp, to), view(h, h->cp, h->co), h->slot_of, cells_occupancy_limit(h), h->stream);
+	h->occ_limit = cells_occupancy_limit(h);
+	const int nl = launch_cell_build(sc, h->cb, view(h, tp, to), view(h, h->cp, h->co), h->slot_of, h->occ_limit, h->stream);
 	prof_end(h, PP_K_CELLS, nl);
 	CUDA_OK(h, cudaGetLastError());
 	h->cells_valid = true;

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ 
 	{ // weight in the acceptance estimator: 1 / P(this displacement stays inside a uniformly shifted cell)
 		const double keep = __dmul_rn(__dmul_rn(__dsub_rn(1., __dmul_rn(fabs(pr.dx), sc.inv_w[0])), __dsub_rn(1., __dmul_rn(fabs(pr.dy), sc.inv_w[1]))),
 				__dsub_rn(1., __dmul_rn(fabs(pr.dz), sc.inv_w[2])));
-		pr.wfix = (unsigned int) (unsigned long long) __dmul_rn(__ddiv_rn(1., keep), 16777216.0);
+		// a displacement comparable to the cell width (keep -> 0) must not wrap the 2^-24 fixed point: weights are capped at 128
+		pr.wfix = (unsigned int) (unsigned long long) __dmul_rn(__ddiv_rn(1., fmax(keep, 0.0078125)), 16777216.0);
 	}
 	const double theta = __dmul_rn(u32_to_unit(y.x), sc.theta_max);
 	pr.u_acc = __dmul_rn((double) ((((unsigned long long) y.y) << 21) | (((unsigned long long) y.z) >> 11)), 1.0 / 9007199254740992.0);

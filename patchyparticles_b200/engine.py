@@ -37,7 +37,8 @@ class Observables(C.Structure):
     _fields_ = [("step", C.c_longlong), ("N", C.c_int), ("box", C.c_double * 3), ("energy", C.c_double),
                 ("tries", C.c_longlong * N_MOVES), ("accepted", C.c_longlong * N_MOVES),
                 ("confined", C.c_longlong), ("overlapped", C.c_longlong), ("acceptance_roto", C.c_double),
-                ("pair_checks", C.c_longlong), ("n_side", C.c_int * 3)]
+                ("pair_checks", C.c_longlong), ("n_side", C.c_int * 3),
+                ("volume", C.c_double)]
 
 
 def library_path():

@@ -254,6 +254,9 @@ def ref_lib():
     L.ref_stream_pos.restype = C.c_long
     L.ref_draws.restype = C.c_long
     L.ref_seed.argtypes = [C.c_long]
+    L.ref_random_vector_on_sphere.argtypes = [_dp]
+    L.ref_gram_schmidt.argtypes = [_dp]
+    L.ref_volume.restype = C.c_double
     _ref = L
     return L
 
@@ -378,6 +381,44 @@ class RefSystem:
         a = np.zeros(8, dtype=np.int32)
         self.L.ref_counters(t, a)
         return t, a
+
+    def run_steps(self, n):
+        """n calls of do_ensemble (main.c:119), drawing from the harness' POSIX drand48"""
+        self.L.ref_run_steps(int(n))
+
+    def run_moves(self, n):
+        self.L.ref_run_moves(int(n))
+
+    def check_energy(self):
+        self.L.ref_check_energy()
+
+    def box_move(self, kind, uniforms):
+        """One MC_change_volume (kind 'volume', MC.c:450-513) or MC_change_Lx (kind 'Lx', MC.c:515-585) fed with the
+        given uniforms in the reference's draw order -> (accepted, uniforms consumed, box, energy, cells)."""
+        slot = 6 if kind == "volume" else 7
+        before = int(self.counters()[1][slot])
+        self.set_stream(uniforms)
+        if kind == "volume":
+            self.L.ref_volume_move()
+        else:
+            self.L.ref_Lx_move()
+        used = int(self.L.ref_stream_pos())
+        self.set_stream(None)
+        return int(self.counters()[1][slot]) - before, used, self.box(), self.running_energy(), self.cells()
+
+    def random_vector_on_sphere(self, uniforms):
+        """utils.c:115-131 fed with the given uniforms -> (axis, uniforms consumed)"""
+        out = np.zeros(3)
+        self.set_stream(uniforms)
+        self.L.ref_random_vector_on_sphere(out)
+        used = int(self.L.ref_stream_pos())
+        self.set_stream(None)
+        return out, used
+
+    def gram_schmidt(self, m):
+        out = np.ascontiguousarray(m, dtype=np.float64).reshape(9).copy()
+        self.L.ref_gram_schmidt(out)
+        return out.reshape(3, 3)
 
 
 def run_generator(N, rho, out_path):

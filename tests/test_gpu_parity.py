@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, replay_box_moves
 
 pytestmark = pytest.mark.gpu
 
@@ -354,4 +354,95 @@ def test_Lx_move_vs_port(pp, oracle):
         assert -e.observables().energy == pb
         seen.add(acc_g)
     assert seen == {-1, 0, 1}
+    e.close()
+
+
+# ---- pins against the unmodified reference added in round 2 ------------------------------------------------------
+def test_warm_bonded_golden(pp):
+    """Bonded state equilibrated by the reference (delta 0.25, cosmax 0.8): its decisions on 8192 frozen and 4096 sequential
+    proposals, hundreds accepted uphill through u < exp(-dE / T) (MC.c:332), bit for bit including the final state."""
+    g = load_golden("warm1000")
+    e = make_engine(pp, g["params"])
+    e.upload(g["box"], g["r"], g["orient"])
+    assert e.total_bonds() == (-g["energy"][0], 0)
+    assert np.array_equal(e.bond_counts(), g["bond_counts"])
+    dE, ov, acc = e.eval_proposals(g["prop_idx"], g["prop_disp"], g["prop_orient"], g["prop_u"])
+    assert np.array_equal(ov, g["prop_overlap"]) and np.array_equal(dE, g["prop_dE"]) and np.array_equal(acc, g["prop_accept"])
+    assert ((dE > 0) & (acc == 1)).sum() >= 300
+    n = len(g["seq_dE"])
+    dE, ov, acc = e.eval_proposals(g["prop_idx"][:n], g["prop_disp"][:n], g["prop_orient"][:n], g["prop_u"][:n], commit=True)
+    assert np.array_equal(ov, g["seq_overlap"]) and np.array_equal(dE, g["seq_dE"]) and np.array_equal(acc, g["seq_accept"])
+    r, m = e.download()
+    assert np.array_equal(r, g["seq_r"]) and np.array_equal(m, g["seq_orient"])
+    assert e.observables().energy == g["seq_energy"][0] and e.total_bonds() == (-g["seq_energy"][0], 0)
+    e.close()
+
+
+@pytest.mark.parametrize("tag", ["vol", "vol_grid", "lx", "lx_grid"])
+def test_box_moves_golden(pp, tag):
+    """pp_volume_move / pp_Lx_move against the reference's own MC_change_volume (MC.c:450-513) and MC_change_Lx
+    (MC.c:515-585) driven with recorded uniforms: result, box (bit for bit) and energy after each of 60 moves, including
+    moves that cross the re-grid threshold (MC.c:481-485) and Lx moves rejected by the Lyz window (MC.c:527-530)."""
+    g = load_golden("box_moves")
+    P, rfm, lx_max, lyz_min, lyz_max = g[f"{tag}_keys"]
+    if tag.startswith("vol"):
+        e = make_engine(pp, g[f"{tag}_params"], ensemble=5, P=float(P), rescale_factor_max=float(rfm))
+    else:
+        e = make_engine(pp, g[f"{tag}_params"], Lx_move=1, Lx_change_max=float(lx_max), Lyz_min=float(lyz_min), Lyz_max=float(lyz_max))
+    e.upload(g[f"{tag}_box"], g[f"{tag}_r"], g[f"{tag}_orient"])
+    assert e.total_bonds() == (-g[f"{tag}_energy0"][0], 0)
+
+    def observe():
+        o = e.observables()
+        return np.array(o.box), o.energy, None
+
+    replay_box_moves(g, tag, lambda P_, rfm_, a, b, c: e.volume_move(a, b, c), lambda mx, lo, hi, a, b: e.Lx_move(a, b), observe)
+    n_acc = int((g[f"{tag}_result"] == 1).sum())
+    o = e.observables()
+    slot = 6 if tag.startswith("vol") else 7
+    assert o.tries[slot] == len(g[f"{tag}_u"]) and o.accepted[slot] == n_acc
+    r, _ = e.download()
+    assert np.abs(r - g[f"{tag}_r_final"]).max() < 1e-12  # (a rejected move keeps the old bits here; the reference divides back)
+    b, ov, ok = e.check_energy()
+    assert ok and -b == g[f"{tag}_energies"][-1]
+    e.sweep(3)  # and the engine goes on from the final box
+    assert e.check_energy()[2]
+    e.close()
+
+
+def test_orthonormalise_vs_reference(pp):
+    """K6 (k_orthonormalise inside pp_check_energy, MC.c:774) against the reference's gram_schmidt (utils.c:91-113) on
+    drifted matrices: bit-equal."""
+    g = load_golden("helpers")
+    m_in, want = g["gs_in"], g["gs_out"]
+    n = len(m_in)
+    side = int(np.ceil(n ** (1 / 3)))
+    grid = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n]
+    box = np.full(3, 3.0 * side)
+    e = pp.Engine()
+    e.upload(box, 3.0 * grid + 0.7, m_in)  # isolated particles: the energy does not care about their orientation
+    assert e.total_bonds() == (0, 0)
+    e.check_energy()
+    _, m = e.download()
+    assert np.array_equal(m, want)
+    e.close()
+
+
+def test_box_move_into_too_small_box_is_rejected(pp):
+    """A trial box that cannot hold two cells per side is counted and rejected with nothing touched (the reference clamps
+    its grid to 3 cells there, cells.c:24-27); the run goes on."""
+    rng = np.random.default_rng(2)
+    box = np.array([2.3, 6.0, 6.0])  # two cells of 1.15 > r_cut = 1.119 along x
+    r = np.array([[0.2, 0.3, 0.4], [1.5, 2.0, 2.5], [0.3, 4.0, 1.0], [1.4, 5.0, 4.5]])
+    m = pp.random_fluid(64, 0.2, seed=1)[2][:4]
+    e = pp.Engine(ensemble=5, P=50.0, rescale_factor_max=0.5, temperature=1.0)
+    e.upload(box, r, m)
+    e.total_bonds()
+    acc = e.volume_move(0.1, 0.0, 1e-9)  # compress x by exp(-0.25): 1.79 < 2 r_cut
+    o = e.observables()
+    assert acc == 0 and np.array_equal(np.array(o.box), box) and o.tries[6] == 1 and o.accepted[6] == 0
+    r2, _ = e.download()
+    assert np.array_equal(r2, r)
+    e.sweep(20)  # NPT steps with more such trials in them
+    assert e.check_energy()[2]
     e.close()

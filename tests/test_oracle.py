@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, replay_box_moves
 
 GOLDEN_SETS = ["fcc", "bcc", "gen1000_rho0.1", "gen2000_rho0.5"]
 
@@ -112,6 +112,75 @@ def test_port_proposals_golden(oracle, name):
     r, m = p.state()
     assert np.array_equal(r, g["seq_r"]) and np.array_equal(m, g["seq_orient"])
     assert -p.total_bonds()[0] == g["seq_energy"][0]
+
+
+def test_port_warm_bonded_golden(oracle):
+    """A bonded state point equilibrated by the reference (delta 0.25, cosmax 0.8): the reference's decisions on 8192 frozen
+    and 4096 sequential proposals, hundreds of them accepted uphill through u < exp(-dE / T) (MC.c:332)."""
+    g = load_golden("warm1000")
+    delta, cosmax, T = g["params"]
+    uphill = (g["prop_dE"] > 0) & (g["prop_accept"] == 1)
+    assert uphill.sum() >= 300 and ((g["seq_dE"] > 0) & (g["seq_accept"] == 1)).sum() >= 150  # the golden set does exercise the draw
+    assert ((g["prop_dE"] > 0) & (g["prop_accept"] == 0) & (g["prop_overlap"] == 0)).sum() >= 1000
+    p = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    assert p.total_bonds() == (-g["energy"][0], 0)
+    assert np.array_equal(p.bond_counts()[0], g["bond_counts"])
+    dE, ov, acc = p.eval_proposals(g["prop_idx"], g["prop_disp"], g["prop_orient"], g["prop_u"])
+    assert np.array_equal(dE, g["prop_dE"]) and np.array_equal(ov, g["prop_overlap"]) and np.array_equal(acc, g["prop_accept"])
+    n = len(g["seq_dE"])
+    dE, ov, acc = p.eval_proposals(g["prop_idx"][:n], g["prop_disp"][:n], g["prop_orient"][:n], g["prop_u"][:n], commit=True)
+    assert np.array_equal(dE, g["seq_dE"]) and np.array_equal(ov, g["seq_overlap"]) and np.array_equal(acc, g["seq_accept"])
+    r, m = p.state()
+    assert np.array_equal(r, g["seq_r"]) and np.array_equal(m, g["seq_orient"])
+    assert -p.total_bonds()[0] == g["seq_energy"][0]
+
+
+@pytest.mark.parametrize("tag", ["vol", "vol_grid", "lx", "lx_grid"])
+def test_port_box_moves_golden(oracle, tag):
+    """The restated volume / Lx moves against the reference's own MC_change_volume (MC.c:450-513) and MC_change_Lx
+    (MC.c:515-585, including the exp(+dE/T) test of MC.c:562), driven move by move with recorded uniforms."""
+    g = load_golden("box_moves")
+    res, cells = g[f"{tag}_result"], g[f"{tag}_cells"]
+    assert set(res.tolist()) >= ({0, 1} if tag.startswith("vol") else {-1, 0, 1})
+    if tag.endswith("_grid"):
+        assert (cells != g[f"{tag}_cells0"]).any()  # the sequence does cross the re-grid threshold (MC.c:481-485)
+    delta, cosmax, T = g[f"{tag}_params"]
+    p = oracle.PortSystem(g[f"{tag}_box"], g[f"{tag}_r"], g[f"{tag}_orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    state = {"bonds": p.total_bonds()[0], "ov": 0}
+    assert -state["bonds"] == g[f"{tag}_energy0"][0]
+
+    def vol(P, rfm, u0, u1, u2):
+        acc, state["bonds"], state["ov"] = p.volume_move(P, rfm, u0, u1, u2, state["bonds"])
+        return acc
+
+    def lx(lx_max, lo, hi, u0, u1):
+        acc, state["bonds"], state["ov"] = p.Lx_move(lx_max, lo, hi, u0, u1, state["bonds"])
+        return acc
+
+    replay_box_moves(g, tag, vol, lx, lambda: (p.box(), -float(state["bonds"]), state["ov"]))
+    assert np.array_equal(p.state()[0], g[f"{tag}_r_final"])  # the restatement divides back like the reference: same bits
+
+
+def test_port_helpers_golden(oracle):
+    """Marsaglia's rejection loop + axis (utils.c:115-131) and gram_schmidt (utils.c:91-113) against what the reference's
+    own functions returned for recorded inputs."""
+    g = load_golden("helpers")
+    L = oracle.port_lib()
+    axis = np.zeros(3)
+    for u, want, used in zip(g["sphere_u"], g["sphere_axis"], g["sphere_used"]):
+        k = 0
+        while True:  # utils.c:120-124
+            ran1, ran2 = 1. - 2. * u[k], 1. - 2. * u[k + 1]
+            k += 2
+            if ran1 * ran1 + ran2 * ran2 < 1.:
+                break
+        assert k == used
+        L.ppo_axis_from_pair(ran1, ran2, axis)
+        assert np.array_equal(axis, want)
+    for m_in, want in zip(g["gs_in"], g["gs_out"]):
+        m = np.ascontiguousarray(m_in).reshape(9).copy()
+        L.ppo_gram_schmidt(m)
+        assert np.array_equal(m.reshape(3, 3), want)
 
 
 def test_port_vs_reference_library(oracle, tmp_path):
@@ -267,7 +336,7 @@ def test_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(pkg.library_path())
     for name in sorted(declared):
         assert hasattr(lib, name), name
-    assert lib.pp_abi_version() == 1
+    assert lib.pp_abi_version() == 2
     assert ctypes.sizeof(pkg.Params) >= 120
 
 

@@ -84,10 +84,145 @@ def bond_lists():
     np.savez_compressed(os.path.join(GOLD, "bond_lists.npz"), **out)
 
 
+WARM = dict(KF_delta=0.25, KF_cosmax=0.8, Temperature=0.3)
+
+
+def warm():
+    """tests/golden/warm1000.npz: a bonded, equilibrated state point (delta = 0.25, cosmax = 0.8, T = 0.3, rho = 0.4) made by
+    the reference itself (3000 do_NVT steps from its generator's output), then the reference's decisions on seeded
+    proposal lists from that state, taken at T = 0.6: hundreds of moves are accepted uphill through u < exp(-dE / T) (MC.c:332)."""
+    tmp = "/tmp/_golden_gen.rrr"
+    O.run_generator(1000, 0.4, tmp)
+    ref = O.RefSystem(tmp, Disp_max=0.2, Theta_max=0.3, Seed=4242, **WARM)
+    ref.set_running_energy(ref.total_energy()[0])  # main.c:55-61
+    ref.run_steps(3000)
+    r, m = ref.state()
+    e, ov = ref.total_energy()
+    counts, _ = ref.bond_counts()
+    assert ov == 0 and e == ref.running_energy()
+    box = ref.box().copy()
+    ref.close()
+    # the decisions below are taken at T = 0.6 on that state, so that a fifth of the uphill proposals passes the draw
+    T_eval = 0.6
+    ref = O.RefSystem(tmp, **dict(WARM, Temperature=T_eval))
+    ref.set_state(r, m)
+    assert ref.total_energy() == (e, 0)
+    out = dict(box=box, r=r, orient=m, energy=np.array([e, ov]), bond_counts=counts,
+               params=np.array([WARM["KF_delta"], WARM["KF_cosmax"], T_eval]), T_equilibration=np.array([WARM["Temperature"]]))
+    rng = np.random.default_rng(11)
+    n = 8192
+    idx, disp, on, u = proposals(rng, ref, m, n, 0.3, 0.5)
+    dE, ovl, acc = ref.eval_proposals(idx, disp, on, u, commit=False)
+    out.update(prop_idx=idx, prop_disp=disp, prop_orient=on, prop_u=u, prop_dE=dE, prop_overlap=ovl, prop_accept=acc)
+    print("warm frozen: accepted", int(acc.sum()), "uphill accepted", int(((dE > 0) & (acc == 1)).sum()), "uphill rejected",
+          int(((dE > 0) & (acc == 0) & (ovl == 0)).sum()), "dE != 0", int((dE != 0).sum()))
+    n_seq = 4096
+    dE, ovl, acc = ref.eval_proposals(idx[:n_seq], disp[:n_seq], on[:n_seq], u[:n_seq], commit=True)
+    r2, m2 = ref.state()
+    e2, _ = ref.total_energy()
+    out.update(seq_dE=dE, seq_overlap=ovl, seq_accept=acc, seq_r=r2, seq_orient=m2, seq_energy=np.array([e2]))
+    print("warm sequential: accepted", int(acc.sum()), "uphill accepted", int(((dE > 0) & (acc == 1)).sum()), "E", e, "->", e2)
+    ref.close()
+    np.savez_compressed(os.path.join(GOLD, "warm1000.npz"), **out)
+
+
+def box_moves():
+    """tests/golden/box_moves.npz: the reference's own MC_change_volume (MC.c:450-513) and MC_change_Lx (MC.c:515-585)
+    driven one move at a time on the warm state, the uniforms of each move supplied in the reference's draw order
+    (dir, volume, acceptance / Lx, acceptance) through the interposed drand48.  Per move: result (1 accepted, 0 rejected,
+    -1 an Lx move rejected by the Lyz window before any rescaling, MC.c:527-530), uniforms consumed (an overlap ends the
+    move before the acceptance draw), box, energy and the reference's cell grid afterwards.  Sequences:
+      vol      NPT, P = 0.5, rescale_factor_max = 2e-3
+      vol_grid the same with r_cut 2e-5 below box / 10: compressions cross the re-grid threshold of MC.c:481-485
+      lx       NVT + Lx_move, Lx_change_max = 0.02, Lyz window +- 0.004 around the start
+      lx_grid  the same with the re-grid threshold of MC.c:548-552 / 577-581 inside a wider window"""
+    g = np.load(os.path.join(GOLD, "warm1000.npz"))
+    tmp = "/tmp/_golden_warm.rrr"
+    O.write_rrr(tmp, 0, g["box"], g["r"], g["orient"].reshape(-1, 9))
+    L0 = float(g["box"][0])
+    d_grid = L0 / 10. * (1. - 2e-5) - 1.
+    out = {}
+    rng = np.random.default_rng(23)
+    n = 60
+    for tag, kind, keys in (
+            ("vol", "volume", dict(Ensemble=5, P=0.5, rescale_factor_max=2e-3, **WARM)),
+            ("vol_grid", "volume", dict(Ensemble=5, P=0.5, rescale_factor_max=2e-3, **dict(WARM, KF_delta=d_grid))),
+            ("lx", "Lx", dict(Lx_move=1, Lx_change_max=0.02, Lyz_min=L0 - 0.004, Lyz_max=L0 + 0.004, **WARM)),
+            ("lx_grid", "Lx", dict(Lx_move=1, Lx_change_max=0.02, Lyz_min=L0 - 0.01, Lyz_max=L0 + 0.01, **dict(WARM, KF_delta=d_grid)))):
+        ref = O.RefSystem(tmp, **keys)
+        # the .rrr text is lossy (output.c:311-313): what the reference parsed back is the configuration of this sequence
+        r, m = ref.state()
+        box0 = ref.box().copy()
+        e, ov = ref.total_energy()
+        assert ov == 0
+        ref.set_running_energy(e)
+        u = rng.random((n, 3 if kind == "volume" else 2))
+        if kind == "volume":
+            u[::3, 1] = 0.5 + 0.5 * u[::3, 1]   # a third of the moves are expansions for certain ...
+            u[::3, 2] *= 0.2                     # ... with acceptance draws that exp(-P dV / T + (N + 1) ln f) can pass
+        res = np.zeros(n, dtype=np.int32)
+        used = np.zeros(n, dtype=np.int32)
+        boxes = np.zeros((n, 3))
+        energies = np.zeros(n)
+        cells = np.zeros((n, 3), dtype=np.int32)
+        cells0 = ref.cells().copy()
+        V = float(ref.L.ref_volume())
+        prev = box0
+        for k in range(n):
+            a, c, bx, en, cl = ref.box_move(kind, u[k])
+            if kind == "Lx" and a == 0 and c == 1:
+                ly = np.sqrt(V / (prev[0] + (u[k, 0] - 0.5) * keys["Lx_change_max"]))
+                if ly < keys["Lyz_min"] or ly > keys["Lyz_max"]:
+                    a = -1
+            res[k], used[k], boxes[k], energies[k], cells[k] = a, c, bx, en, cl
+            prev = bx.copy()
+        r2, _ = ref.state()
+        e2, ov2 = ref.total_energy()
+        assert ov2 == 0 and e2 == energies[-1]
+        out.update({f"{tag}_r": r, f"{tag}_orient": m, f"{tag}_box": box0, f"{tag}_energy0": np.array([e]),
+                    f"{tag}_params": np.array([keys["KF_delta"], keys["KF_cosmax"], keys["Temperature"]]),
+                    f"{tag}_keys": np.array([keys.get("P", 0.), keys.get("rescale_factor_max", 0.), keys.get("Lx_change_max", 0.),
+                                             keys.get("Lyz_min", 0.), keys.get("Lyz_max", 0.)]),
+                    f"{tag}_u": u, f"{tag}_result": res, f"{tag}_used": used, f"{tag}_boxes": boxes, f"{tag}_energies": energies,
+                    f"{tag}_cells0": cells0, f"{tag}_cells": cells, f"{tag}_r_final": r2})
+        print("box moves", tag, "results", np.bincount(res + 1, minlength=3), "(-1, 0, 1) draws used", np.bincount(used), "cells", cells0, "->",
+              cells[-1], "E", e, "->", e2, "distinct energies", len(set(energies.tolist())))
+        ref.close()
+    np.savez_compressed(os.path.join(GOLD, "box_moves.npz"), **out)
+
+
+def helpers():
+    """tests/golden/helpers.npz: the reference's random_vector_on_sphere (utils.c:115-131) fed with recorded uniforms
+    (axis + number of uniforms consumed) and its gram_schmidt (utils.c:91-113) on perturbed orientation matrices."""
+    tmp = "/tmp/_golden_gen.rrr"
+    O.run_generator(1000, 0.1, tmp)
+    ref = O.RefSystem(tmp)
+    rng = np.random.default_rng(3)
+    n = 512
+    u = rng.random((n, 16))
+    axis = np.zeros((n, 3))
+    used = np.zeros(n, dtype=np.int32)
+    for k in range(n):
+        axis[k], used[k] = ref.random_vector_on_sphere(u[k])
+    _, m = ref.state()
+    gs_in = m[:n] + 1e-3 * (rng.random((n, 3, 3)) - 0.5)   # drifted matrices, as MC_check_energy finds them after many moves
+    gs_in[::7] = m[:n][::7] * (1. + 1e-13)                  # and nearly exact ones
+    gs_out = np.array([ref.gram_schmidt(x) for x in gs_in])
+    ref.close()
+    print("helpers: uniforms consumed per axis", np.bincount(used))
+    np.savez_compressed(os.path.join(GOLD, "helpers.npz"), sphere_u=u, sphere_axis=axis, sphere_used=used, gs_in=gs_in, gs_out=gs_out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "helpers":
+        return helpers()
     if len(sys.argv) > 1 and sys.argv[1] == "bond_lists":
         return bond_lists()
+    if len(sys.argv) > 1 and sys.argv[1] == "warm":
+        return warm()
+    if len(sys.argv) > 1 and sys.argv[1] == "box_moves":
+        return box_moves()
     one("fcc", os.path.join(REF, "fcc.rrr"), {"a": {}, "b": {"KF_cosmax": 0.92}}, n_prop=2048, T=0.11)
     one("bcc", os.path.join(REF, "bcc.rrr"), {"a": {}, "b": {"KF_delta": 0.135}}, n_prop=1024)
     tmp = "/tmp/_golden_gen.rrr"
@@ -98,6 +233,9 @@ def main():
     # known answers for the large generator outputs (configuration regenerated at test time by the
     # reference's deterministic generator when oracle/_ref/ is present)
     bond_lists()
+    warm()
+    box_moves()
+    helpers()
     known = {}
     for N, rho in [(32768, 0.3), (65536, 0.5)]:
         O.run_generator(N, rho, tmp)
