@@ -75,7 +75,7 @@ static void die(host_output *out, const char *fmt, ...) {
 
 #define PP_CALL(out, h, call) \
 	do { \
-		if((call) != 0) die(out, "%s\n", pp_last_error(h)); \
+		if((call) != 0) die(out, "%s\n", pp_group_last_error(h)); \
 	} while(0)
 
 static FILE *open_or_die(host_output *out, const char *name, const char *mode, const char *what) {
@@ -84,10 +84,10 @@ static FILE *open_or_die(host_output *out, const char *name, const char *mode, c
 	return f;
 }
 
-static void save_configuration(host_output *out, pp_handle *h, int N, llint step, const char *name, double *r, double *orient) {
+static void save_configuration(host_output *out, pp_group *h, int N, llint step, const char *name, double *r, double *orient) {
 	pp_observables obs;
-	PP_CALL(out, h, pp_download(h, r, orient));
-	PP_CALL(out, h, pp_get_observables(h, &obs, 0));
+	PP_CALL(out, h, pp_group_download(h, r, orient));
+	PP_CALL(out, h, pp_group_get_observables(h, &obs, 0));
 	if(pph_rrr_write(name, step, N, obs.box, r, orient) != 0) die(out, "File '%s' is not writable\n", name);
 }
 
@@ -95,11 +95,11 @@ static void save_configuration(host_output *out, pp_handle *h, int N, llint step
 /* output_print_bonds (output.c:213-268): N, then two lines per particle -- "index n_bonds" and the indices of the bonded
  * neighbours, each followed by a blank (possibly an empty line).  The reference builds the second line with an
  * overlapping sprintf (output.c:250, undefined behaviour); here it is simply the list, cell by cell. */
-static void print_bonds(host_output *out, pp_handle *h, int N, llint step) {
+static void print_bonds(host_output *out, pp_group *h, int N, llint step) {
 	char name[1100];
 	snprintf(name, sizeof(name), "%s/bonds_%lld.dat", out->bonds_folder, step);
-	if(pp_bond_lists(h, PP_HOST_MAX_BONDS, out->bond_counts, out->bond_neighbours)) {
-		fprintf(stderr, "%s\n", pp_last_error(h));
+	if(pp_group_bond_lists(h, PP_HOST_MAX_BONDS, out->bond_counts, out->bond_neighbours)) {
+		fprintf(stderr, "%s\n", pp_group_last_error(h));
 		exit(1);
 	}
 	FILE *f = fopen(name, "w");
@@ -117,9 +117,9 @@ static void print_bonds(host_output *out, pp_handle *h, int N, llint step) {
 	fclose(f);
 }
 
-static void print_observables(host_output *out, pp_handle *h, const pp_params *prm, llint step) {
+static void print_observables(host_output *out, pp_group *h, const pp_params *prm, llint step) {
 	pp_observables o;
-	PP_CALL(out, h, pp_get_observables(h, &o, 1)); /* counters are reset after each print (output.c:189) */
+	PP_CALL(out, h, pp_group_get_observables(h, &o, 1)); /* counters are reset after each print (output.c:189) */
 	const double V = o.volume; /* System.V, output.c:131 */
 	const double E = (o.N > 0) ? o.energy / o.N : 0.;
 	fprintf(out->energy, "%lld %lf\n", step, E);
@@ -256,19 +256,34 @@ int main(int argc, char *argv[]) {
 	if(pph_get_int(in, "Shift_every", &itmp, 0)) prm.shift_every = itmp;
 	if(pph_get_int(in, "Lx_reference_sign", &itmp, 0)) prm.Lx_reference_sign = itmp;
 
-	pp_handle *h = NULL;
-	if(pp_create(&prm, &h) != 0) die(&out, "%s\n", pp_last_error(h));
-	PP_CALL(&out, h, pp_upload(h, N, box, r, orient));
+	/* GPUs = n: the system is split into n x-slabs, slab k on device GPU_device + k (GPU_devices = a b c ... names them
+	 * explicitly; a device may be listed several times).  One host thread drives all of them (pp_group). */
+	int n_gpus = 1, devices[64];
+	if(pph_get_int(in, "GPUs", &itmp, 0)) n_gpus = itmp;
+	if(n_gpus < 1 || n_gpus > 64) die(&out, "GPUs = %d out of range (1 .. 64)\n", n_gpus);
+	for(int k = 0; k < n_gpus; k++) devices[k] = prm.device + k;
+	{
+		char list[512];
+		if(pph_get_string(in, "GPU_devices", list, sizeof(list), 0)) {
+			int k = 0;
+			for(char *tok = strtok(list, " ,\t"); tok != NULL && k < n_gpus; tok = strtok(NULL, " ,\t")) devices[k++] = atoi(tok);
+			if(k != n_gpus) die(&out, "GPU_devices lists %d devices, GPUs = %d\n", k, n_gpus);
+		}
+	}
+	pp_group *h = NULL;
+	if(pp_group_create(&prm, n_gpus, devices, &h) != 0) die(&out, "%s\n", h ? pp_group_last_error(h) : "pp_group_create failed");
+	if(n_gpus > 1) log_msg(&out, "Running on %d x-slabs\n", n_gpus);
+	PP_CALL(&out, h, pp_group_upload(h, N, box, r, orient));
 	{
 		pp_observables o;
-		PP_CALL(&out, h, pp_get_observables(h, &o, 0));
+		PP_CALL(&out, h, pp_group_get_observables(h, &o, 0));
 		log_msg(&out, "Cells per side: (%d, %d, %d), total: %d\n", o.n_side[0], o.n_side[1], o.n_side[2], o.n_side[0] * o.n_side[1] * o.n_side[2]);
 	}
 
 	/* ---- initial energy and overlap check (main.c:55-64) ------------------------------------- */
 	llint bonds = 0;
 	int overlap = 0;
-	PP_CALL(&out, h, pp_total_bonds(h, &bonds, &overlap));
+	PP_CALL(&out, h, pp_group_total_bonds(h, &bonds, &overlap));
 	if(overlap) die(&out, "Initial configuration contains an overlap, aborting\n");
 	log_msg(&out, "Initial energy: %lf\n", (N > 0) ? -(double) bonds / N : 0.);
 
@@ -292,9 +307,9 @@ int main(int argc, char *argv[]) {
 			if(step != 0) { /* MC_check_energy + cells_check (main.c:85-87) */
 				llint scratch;
 				int ov, ok;
-				PP_CALL(&out, h, pp_check_energy(h, &scratch, &ov, &ok));
+				PP_CALL(&out, h, pp_group_check_energy(h, &scratch, &ov, &ok));
 				if(ov) die(&out, "\nComputing energy from scratch resulted in an overlap, aborting\n");
-				if(!ok) die(&out, "\nEnergy check failed: %s\n", pp_last_error(h));
+				if(!ok) die(&out, "\nEnergy check failed: %s\n", pp_group_last_error(h));
 			}
 		}
 		if(step > 0 && step % out.save_every == 0) {
@@ -309,8 +324,8 @@ int main(int argc, char *argv[]) {
 		if(ns < next) next = ns;
 		llint chunk = next - step;
 		if(chunk > 64) chunk = 64;
-		PP_CALL(&out, h, pp_sweep(h, chunk));
-		PP_CALL(&out, h, pp_sync(h));
+		PP_CALL(&out, h, pp_group_sweep(h, chunk));
+		PP_CALL(&out, h, pp_group_sync(h));
 		step += chunk;
 	}
 
@@ -318,13 +333,13 @@ int main(int argc, char *argv[]) {
 	save_configuration(&out, h, N, step, out.conf_last, r, orient);
 	{
 		pp_observables o;
-		PP_CALL(&out, h, pp_get_observables(h, &o, 0));
+		PP_CALL(&out, h, pp_group_get_observables(h, &o, 0));
 		printf("%lld %lf %lf", step, (o.N > 0) ? o.energy / o.N : 0., o.energy);
 		if(prm.ensemble != PP_NVT) printf(" %lf", o.N / o.volume);
 		printf("\n");
 	}
 
-	pp_destroy(h);
+	pp_group_destroy(h);
 	free(r);
 	free(orient);
 	free(out.bond_counts);

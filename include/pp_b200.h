@@ -58,14 +58,17 @@ typedef struct pp_params {
 	int Lx_reference_sign;      /* 1: reproduce exp(+dE/T) of MC.c:562; 0: Metropolis exp(-dE/T) */
 	uint64_t seed;              /* Seed                                             system.c:71-75 */
 	int device;                 /* CUDA device ordinal */
-	int lanes_per_cell;         /* kernel choice of the sweep.  0 = automatic: by system size, either the tile kernel alone or the
-	                               hybrid routing (sparsely populated cells on the thread-per-cell kernel, crowded ones on its
-	                               8-lane configuration, concurrently); 1 = thread-per-cell kernel wherever a cell fits it;
-	                               4, 8, 16, 32 = tile kernel of that width (for the crowded cells if cells_max_occupancy > 0) */
-	int cell_lanes;             /* lanes per cell of the thread-per-cell kernel for the sparsely populated cells: 0 = 1, or 1, 2, 4, 8 */
-	int cells_max_occupancy;    /* hybrid routing: cells with at most this many particles go to the thread-per-cell kernel;
+	int lanes_per_cell;         /* kernel choice of the sweep.  0 = automatic: by system size, either the tile kernel alone or one fused
+	                               launch per colour pass in which sparsely populated cells run on one thread per cell, the middle
+	                               range on 4 lanes and the crowded cells on 8 lanes per cell; 1 = one thread per cell wherever a
+	                               cell fits it; 4, 8, 16, 32 = tile kernel of that width for every cell */
+	int cell_lanes;             /* 2, 4, 8: that many lanes per cell for the sparsely populated range (the three ranges then run as
+	                               three launches); 0 or 1: one thread per cell inside the fused launch */
+	int cells_max_occupancy;    /* cells with at most this many particles run on one thread per cell;
 	                               -1 = automatic (3 for N >= 800k, 2 for N >= 400k, 1 for N >= 150k, else 0), 0 = tile kernel only */
 	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
+	int cells_mid_occupancy;    /* cells with more particles than cells_max_occupancy and at most this many run on 4 lanes per cell, the
+	                               more crowded ones on 8; -1 = automatic */
 } pp_params;
 
 typedef struct pp_observables {
@@ -82,6 +85,7 @@ typedef struct pp_observables {
 	long long pair_checks;               /* pair tests executed by the sweep kernel */
 	int n_side[3];                       /* current (even) cell grid */
 	double volume;                       /* System.V (system.c:198, MC.c:500): what density.dat divides by, output.c:131 */
+	unsigned long long w_tries, w_accepted; /* the sums behind acceptance_roto (fixed point 2^-24): additive over the engines of a decomposition */
 } pp_observables;
 
 void pp_default_params(pp_params *p);
@@ -170,7 +174,7 @@ int pp_reset_kernel_stats(pp_handle *h);
  *     pp_slab_sweep_end()
  * Records are 13 doubles (x, y, z, id, orientation[9]); halo views are contiguous slices of the
  * engine's position (double4), orientation (9 doubles) and fixed-point shadow (uint2) arrays.  All
- * pointers returned here are DEVICE pointers.  NVT only. */
+ * pointers returned here are DEVICE pointers. */
 int pp_slab_setup(pp_handle *h, int rank, int world);
 int pp_slab_range(pp_handle *h, int *x0, int *x1, int *nx, int *n_local);
 int pp_slab_sweep_begin(pp_handle *h, int *exchange);
@@ -179,23 +183,75 @@ int pp_slab_inbox(pp_handle *h, int side, int count, void **dev);
 int pp_slab_sweep_rebuild(pp_handle *h);
 int pp_slab_pass_block(pp_handle *h, int cx);
 int pp_slab_halo(pp_handle *h, int side, int recv, void **pos, void **ori, void **posf, int *count);
-/* Halo refresh over peer memory, for engines on the GPUs of one NVLink / NVSwitch node (replaces the
- * library transfers of the pp_slab_halo slices).  Every engine exports a mailbox block as a 64-byte
- * cudaIpcMemHandle_t after pp_upload, the driver hands each engine the handles of its left and right
- * neighbour, and pp_slab_refresh(side) then (1) stores the engine's first (side 0) / last (side 1) owned
- * layer into the neighbour's mailbox and publishes a sequence number there, (2) waits on the device for the
- * matching number in its own mailbox and moves it into its right (side 0) / left (side 1) halo layer.  Nothing
- * synchronises with the host; a neighbour that never shows up is reported by pp_sync after 20 s. */
-int pp_slab_peer_export(pp_handle *h, void *ipc_handle_64);
-int pp_slab_peer_connect(pp_handle *h, const void *left_handle_64, const void *right_handle_64);
-int pp_slab_refresh(pp_handle *h, int side);
+/* ---- the data path of the decomposition: stores into the neighbouring engine's memory, no mailbox copy -----------
+ * Engines on the GPUs of one NVLink / NVSwitch node (or several engines on one GPU).  Every engine keeps its whole
+ * device state in one allocation and describes it with a pp_peer_info (a CUDA IPC handle + offsets); the driver hands
+ * each engine the descriptions of its left and right neighbour (pp_slab_peer_connect).  From then on
+ *   - the sweep kernels themselves keep the neighbours' halo layers current: the thread that commits an accepted move
+ *     of a particle in the engine's first (last) owned layer also stores the new position, orientation and shadow into
+ *     the left (right) neighbour's halo copy over NVLink -- no push / pull kernels, nothing to overlap;
+ *   - neighbouring engines only exchange a phase number (a release store into the neighbour's control words after the
+ *     rebuild and after each block of four colour passes, an acquire spin in a one-thread kernel before the block that
+ *     needs the neighbour's data); nothing synchronises with the host, a neighbour that never shows up is reported by
+ *     pp_sync after 20 s;
+ *   - at a grid shift the migrating particles and the fresh halo layers travel as 13-double records stored into the
+ *     neighbours' migration mailboxes (pp_slab_migrate), one host synchronisation per shift period.
+ * pp_upload_subset gives an engine only the particles of the layers it holds (owned + halo). */
+typedef struct pp_peer_info {
+	unsigned char ipc[64];              /* cudaIpcMemHandle_t of the engine's arena */
+	unsigned long long off_pos[3];      /* byte offsets inside the arena: position buffers (double4) */
+	unsigned long long off_ori[2];      /* orientation buffers (9 doubles per particle) */
+	unsigned long long off_posf;        /* fixed-point shadows (uint2) */
+	unsigned long long off_mig[2];      /* migration mailboxes: records from the left / right neighbour */
+	unsigned long long off_ctrl;        /* control words: phases completed by the left / right neighbour, migration flags and counts */
+	long long cap_records;              /* records per mailbox */
+} pp_peer_info;
+int pp_slab_peer_export(pp_handle *h, pp_peer_info *info);
+int pp_slab_peer_connect(pp_handle *h, const pp_peer_info *left, const pp_peer_info *right);
 int pp_slab_peer_close(pp_handle *h);
-/* start of a shift period over peer memory: pp_slab_sweep_begin + record exchange + pp_slab_sweep_rebuild in one call */
+/* particles with their global ids (ascending ids are not required); N_global = particles of the whole system.
+ * pp_slab_select marks the particles engine `rank` of `world` has to receive for a given box (layer of each particle
+ * on the unshifted grid, exactly as the engine computes it). */
+int pp_upload_subset(pp_handle *h, int N_global, int n_local, const int *ids, const double *box, const double *r, const double *orient);
+int pp_slab_select(const pp_params *params, int rank, int world, int N, const double *box, const double *r, unsigned char *mine);
+/* start of a shift period: classify on the new grid, store the outgoing records into the neighbours' mailboxes, take in
+ * what they stored here, rebuild the cells.  *migrated = 0 when the current period is still running. */
 int pp_slab_migrate(pp_handle *h, int *migrated);
-/* whole sweeps over peer memory until max_sweeps are done or the next grid shift needs pp_slab_sweep_begin */
+/* whole sweeps (two blocks of four colour passes, each after its neighbour's phase) until max_sweeps are done or the
+ * next grid shift needs pp_slab_migrate */
 int pp_slab_sweeps(pp_handle *h, int max_sweeps, int *done);
+/* box moves under the decomposition (MC_change_volume / MC_change_Lx, MC.c:450-585): every engine rescales and counts
+ * its own layers (pp_slab_box_trial), the driver sums {bonds, overlap} over the engines and every engine takes the
+ * same decision from the same uniforms (pp_slab_box_finish).  kind: PP_VOLUME or PP_LX; u: the move's uniforms in the
+ * reference's draw order.  *status: 0 evaluated; -1 rejected before any work by the Lyz window (MC.c:527-530), -2 because
+ * the trial box cannot hold two cells per side; 2 the trial box needs another cell grid (nothing evaluated: the driver
+ * gathers the configuration, scales it and uploads it again in the trial box). */
+int pp_slab_box_trial(pp_handle *h, int kind, const double *u, long long bonds_running_total, long long *bonds_local, int *overlap_local, int *status);
+int pp_slab_box_finish(pp_handle *h, long long bonds_total, int overlap_any, int *accepted);
 int pp_slab_sweep_end(pp_handle *h);
 int pp_slab_download(pp_handle *h, int *n_owned, int *ids, double *r, double *orient);
+
+
+/* ---- several engines driven from one host thread (the C host's `GPUs = n` key) --------------------------------------
+ * A group is one simulation in n x-slabs, slab k on CUDA device devices[k]; devices may repeat (several slabs on one
+ * GPU run through the same peer stores and orderings, which is how the decomposition is tested on a single GPU).
+ * Same calls and meaning as the single-engine API; orderings between slabs are CUDA events, no process group needed.
+ * n = 1 is a plain engine. */
+typedef struct pp_group pp_group;
+int pp_group_create(const pp_params *params, int n, const int *devices, pp_group **out);
+int pp_group_destroy(pp_group *g);
+const char *pp_group_last_error(const pp_group *g);
+int pp_group_upload(pp_group *g, int N, const double *box, const double *r, const double *orient);
+int pp_group_download(pp_group *g, double *r, double *orient);
+int pp_group_total_bonds(pp_group *g, long long *bonds, int *overlap);
+int pp_group_bond_lists(pp_group *g, int max_per_particle, int *counts, int *neighbours);
+int pp_group_sweep(pp_group *g, long long nsteps);
+int pp_group_sync(pp_group *g);
+int pp_group_get_observables(pp_group *g, pp_observables *obs, int reset);
+int pp_group_check_energy(pp_group *g, long long *bonds_scratch, int *overlap, int *ok);
+int pp_group_volume_move(pp_group *g, double u_dir, double u_vol, double u_acc, int *accepted);
+int pp_group_Lx_move(pp_group *g, double u_lx, double u_acc, int *accepted);
+int pp_group_engine(pp_group *g, int k, pp_handle **h); /* slab k's engine (kernel statistics, tests) */
 
 #ifdef __cplusplus
 }

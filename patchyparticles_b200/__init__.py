@@ -5,9 +5,9 @@ The product is the C-ABI library ``libpatchy_b200.so`` (hand-written sm_100a CUD
 mirror of that ABI used by the tests and by ``bench.py``.  There is no CPU fallback: importing
 :class:`Engine` without the built library, or creating one without a CUDA device, raises.
 """
-from .engine import Engine, Params, Observables, load_library, library_path, LibraryMissing  # noqa: F401
+from .engine import Engine, Group, Params, Observables, load_library, library_path, LibraryMissing  # noqa: F401
 from .rrr import read_rrr, write_rrr, read_rrb, write_rrb, orientation_from_rows  # noqa: F401
 from .configs import fcc_configuration, random_fluid  # noqa: F401
 
-__all__ = ["Engine", "Params", "Observables", "load_library", "library_path", "LibraryMissing",
+__all__ = ["Engine", "Group", "Params", "Observables", "load_library", "library_path", "LibraryMissing",
            "read_rrr", "write_rrr", "read_rrb", "write_rrb", "orientation_from_rows", "fcc_configuration", "random_fluid"]

@@ -74,9 +74,121 @@ __global__ void k_zero_bonds(Counters *counters) {
 	counters->overlap = 0;
 }
 
-int launch_total_bonds(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, Counters *counters, cudaStream_t st) {
-	constexpr int G = 8;
+// ---------------------------------------------------------------------------------------------
+// K3, streaming version (the default): one thread per (particle, column of the half shell).  Every unordered pair
+// is met once: the particle's own cell (slot_q > slot_p) and the 13 neighbour cells with (dx, dy, dz) > (0, 0, 0)
+// in lexicographic order, i.e. five columns -- (0, 0): the rest of the cell and the cell above it in z;
+// (0, +1), (+1, -1), (+1, 0), (+1, +1): three cells each.  Every candidate is first screened in FP32 from the
+// 8-byte fixed-point shadows (the same conservative screen as the sweep: squared distance below r_cut^2 + 2e-3,
+// shadow arithmetic good to 2e-4), so the FP64 position of a particle is fetched only for pairs that may be in
+// range and an orientation matrix only for a pair inside the bonding shell (p's side first; q's matrix only if
+// one of p's patches points at q, as the reference enters its inner loop, MC.c:249-255).  The global overlap
+// flag is polled by every thread: after the first overlap the rest returns at once, like the reference's
+// `while(!overlap_found)` loops (MC.c:488-495, 556-560).  Needs at least four cells per axis (the half shell
+// would meet a cell twice on an axis with two); smaller grids use the tile kernel above.
+// A slab engine counts the pairs of its owned layers among themselves and with the right halo (dx = +1), never
+// with the left halo (dx = -1 is not in the half shell): every cross-boundary pair is counted once, on its left.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBondCellThreads = 256;
+
+__device__ __forceinline__ float shadow16_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); } // 2^23 + low half
+__device__ __forceinline__ float shadow16_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); } // 2^23 + high half
+
+// FP64 pair test of (sp, sq) in the reference's operation order (MC.c:233-262) -> bond count, overlap
+static __device__ __noinline__ void bond_pair_exact(const SimConst &sc, const double4 *__restrict__ pos, const double *__restrict__ ori, int sp, int sq,
+		int &bonds, int &overlap) {
+	const double4 p4 = pos[sp];
+	const Vec3 p = {p4.x, p4.y, p4.z};
+	Vec3 d;
+	const double d2 = min_image(sc, p, pos[sq], d);
+	if(d2 < 1.) overlap = 1;
+	else if(d2 < sc.sqr_rcut) {
+		double m[9];
+#pragma unroll
+		for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
+		bonds += patches_bond_m(sc, d, d2, m, ori + 9ll * sq) ? 1 : 0;
+	}
+}
+
+__global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
+		const int *__restrict__ cell_sorted, const double4 *__restrict__ pos, const double *__restrict__ ori, const uint2 *__restrict__ posf,
+		Counters *counters) {
+	__shared__ int s_bonds, s_overlap;
+	if(threadIdx.x == 0) {
+		s_bonds = 0;
+		s_overlap = 0;
+	}
+	__syncthreads();
+	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
+	int bonds = 0, overlap = 0;
+	const long long t = (long long) blockIdx.x * kBondCellThreads + threadIdx.x;
+	const int sp = (int) (t / 5), col = (int) (t - 5ll * sp);
+	if(sp < sc.N && *((volatile int *) &counters->overlap) == 0) {
+		const int cell = cell_sorted[sp];
+		const int ix = cell / nyz, iy = (cell - ix * nyz) / nz, iz = cell - ix * nyz - iy * nz;
+		if(cell < sc.n_cells && ix >= sc.own_lo && ix < sc.own_hi) {
+			const int dx = col >= 2, dy = col == 0 ? 0 : (col == 1 ? 1 : col - 3);
+			int cx = ix + dx;
+			if(!sc.slab) cx -= (cx >= sc.nxl) ? sc.nxl : 0; // (slab: an owned layer always has its +x neighbour in the held range)
+			int cy = iy + dy;
+			cy += (cy < 0) ? ny : 0;
+			cy -= (cy >= ny) ? ny : 0;
+			const int *cs = cell_start + (cx * ny + cy) * nz;
+			const int zm = iz > 0 ? iz - 1 : nz - 1, zp = iz < nz - 1 ? iz + 1 : 0;
+			// three segments (dz = -1, 0, +1); column 0 has no dz = -1 cell and starts its own cell after the particle itself
+			int sb[3], se[3];
+			sb[0] = col ? cs[zm] : 0;
+			se[0] = col ? cs[zm + 1] : 0;
+			sb[1] = col ? cs[iz] : sp + 1;
+			se[1] = cs[iz + 1];
+			sb[2] = cs[zp];
+			se[2] = cs[zp + 1];
+			const uint2 sh = posf[sp];
+			const float ux = (float) (sc.cell_w[0] / 65535.), uy = (float) (sc.cell_w[1] / 65535.), uz = (float) (sc.cell_w[2] / 65535.);
+			const float wz = (float) sc.cell_w[2];
+			// neighbour minus own position: the 2^23 offsets of the shadow floats cancel in the differences
+			const float px = fmaf(-shadow16_lo(sh.x), ux, (float) dx * (float) sc.cell_w[0]);
+			const float py = fmaf(-shadow16_hi(sh.x), uy, (float) dy * (float) sc.cell_w[1]);
+			const float pz = -shadow16_lo(sh.y) * uz;
+			const float thr = (float) sc.sqr_rcut + 2e-3f;
+#pragma unroll
+			for(int g = 0; g < 3; g++) {
+				const float oz = pz + (float) (g - 1) * wz;
+				for(int sq = sb[g]; sq < se[g]; sq++) {
+					const uint2 qh = posf[sq];
+					const float ax = fmaf(shadow16_lo(qh.x), ux, px), ay = fmaf(shadow16_hi(qh.x), uy, py), az = fmaf(shadow16_lo(qh.y), uz, oz);
+					if(fmaf(az, az, fmaf(ay, ay, ax * ax)) < thr) bond_pair_exact(sc, pos, ori, sp, sq, bonds, overlap);
+				}
+			}
+		}
+	}
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) {
+		bonds += __shfl_xor_sync(0xffffffffu, bonds, o);
+		overlap |= __shfl_xor_sync(0xffffffffu, overlap, o);
+	}
+	if((threadIdx.x & 31) == 0) {
+		if(bonds) atomicAdd(&s_bonds, bonds);
+		if(overlap) atomicOr(&s_overlap, 1);
+	}
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		if(s_bonds) atomicAdd((unsigned long long *) &counters->bonds, (unsigned long long) s_bonds);
+		if(s_overlap) atomicOr(&counters->overlap, 1);
+	}
+}
+
+int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint2 *posf,
+		Counters *counters, cudaStream_t st) {
 	k_zero_bonds<<<1, 1, 0, st>>>(counters);
+	const bool wide = (sc.slab || sc.nxl >= 4) && sc.n_side[1] >= 4 && sc.n_side[2] >= 4;
+	if(wide && posf != nullptr && sc.N > 0) {
+		const long long threads = 5ll * sc.N;
+		k_total_bonds_cells<<<(unsigned) ((threads + kBondCellThreads - 1) / kBondCellThreads), kBondCellThreads, 0, st>>>(sc, cell_start, cell_sorted, pos,
+				ori, posf, counters);
+		return 2;
+	}
+	constexpr int G = 8;
 	const int tiles_per_block = kBondThreads / G;
 	int blocks = (sc.n_cells + tiles_per_block - 1) / tiles_per_block;
 	const int cap = 148 * 16 * 4;
@@ -257,19 +369,22 @@ int launch_proposals(const SimConst &sc, int n, const ProposalIO &io, const int 
 	return 1;
 }
 
-__global__ void k_commit(int slot, const double *__restrict__ disp, const double *__restrict__ orient, double4 *pos, double *ori) {
+__global__ void k_commit(const __grid_constant__ SimConst sc, int slot, const double *__restrict__ disp, const double *__restrict__ orient, double4 *pos,
+		double *ori, uint2 *posf) {
 	if(threadIdx.x == 0) {
 		double4 p = pos[slot];
 		p.x = __dadd_rn(p.x, disp[0]);
 		p.y = __dadd_rn(p.y, disp[1]);
 		p.z = __dadd_rn(p.z, disp[2]);
 		pos[slot] = p;
+		// the shadow follows (rank in the cell unchanged); if the particle left its cell the caller rebuilds the cells anyway
+		posf[slot] = cell_shadow(sc, p.x, p.y, p.z, (int) (posf[slot].y >> 16));
 	}
 	if(threadIdx.x < 9) ori[9ll * slot + threadIdx.x] = orient[threadIdx.x];
 }
 
-int launch_commit(int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, cudaStream_t st) {
-	k_commit<<<1, 32, 0, st>>>(slot, disp3, orient9, pos, ori);
+int launch_commit(const SimConst &sc, int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, uint2 *posf, cudaStream_t st) {
+	k_commit<<<1, 32, 0, st>>>(sc, slot, disp3, orient9, pos, ori, posf);
 	return 1;
 }
 
@@ -315,12 +430,13 @@ int launch_orthonormalise(int N, double *ori, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // upload / download: caller order <-> slot order
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack_state(int N, const double *__restrict__ r, const double *__restrict__ orient, double4 *__restrict__ pos,
-		double *__restrict__ ori, int *__restrict__ pid) {
+__global__ void __launch_bounds__(256) k_pack_state(int N, const double *__restrict__ r, const double *__restrict__ orient, const int *__restrict__ ids,
+		double4 *__restrict__ pos, double *__restrict__ ori, int *__restrict__ pid) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= N) return;
-	pos[i] = make_double4(r[3ll * i], r[3ll * i + 1], r[3ll * i + 2], (double) i);
-	pid[i] = i;
+	const int id = ids ? ids[i] : i; // a slab engine receives a subset of the system with its global ids
+	pos[i] = make_double4(r[3ll * i], r[3ll * i + 1], r[3ll * i + 2], (double) id);
+	pid[i] = id;
 #pragma unroll
 	for(int k = 0; k < 9; k++) ori[9ll * i + k] = orient[9ll * i + k];
 }
@@ -338,9 +454,9 @@ __global__ void __launch_bounds__(256) k_unpack_state(int N, const double4 *__re
 	for(int k = 0; k < 9; k++) orient[9ll * i + k] = ori[9ll * s + k];
 }
 
-int launch_pack_state(int N, const double *r, const double *orient, double4 *pos, double *ori, int *pid, cudaStream_t st) {
+int launch_pack_state(int N, const double *r, const double *orient, const int *ids, double4 *pos, double *ori, int *pid, cudaStream_t st) {
 	if(N == 0) return 0;
-	k_pack_state<<<(N + 255) / 256, 256, 0, st>>>(N, r, orient, pos, ori, pid);
+	k_pack_state<<<(N + 255) / 256, 256, 0, st>>>(N, r, orient, ids, pos, ori, pid);
 	return 1;
 }
 

@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimC
 }
 
 // one warp: exclusive scan of the 8 * kWorkBuckets bins; work_start[colour] marks the colour boundaries
-__global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__ bin_start, int *__restrict__ ranges, int cells_max_occupancy) {
+__global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__ bin_start, int *__restrict__ ranges, int cells_max_occupancy,
+		int cells_mid_occupancy) {
 	__shared__ int s[8 * kWorkBuckets + 1];
 	if(threadIdx.x == 0) {
 		int run = 0;
@@ -187,13 +188,16 @@ __global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__
 	}
 	__syncthreads();
 	for(int b = threadIdx.x; b <= 8 * kWorkBuckets; b += blockDim.x) bin_start[b] = s[b];
-	if(threadIdx.x < 8) { // split each colour's list: crowded cells (tile kernel) first, then cells with <= cells_max_occupancy members
-		const int c = threadIdx.x, m = cells_max_occupancy < kWorkBuckets ? cells_max_occupancy : kWorkBuckets;
-		const int split = s[c * kWorkBuckets + (kWorkBuckets - m)];
-		ranges[4 * c + 0] = s[c * kWorkBuckets];
-		ranges[4 * c + 1] = split;
-		ranges[4 * c + 2] = split;
-		ranges[4 * c + 3] = s[(c + 1) * kWorkBuckets];
+	if(threadIdx.x < 8) { // split each colour's list (occupancy descending): crowded cells, middle range, cells with <= cells_max_occupancy members
+		const int c = threadIdx.x, m1 = cells_max_occupancy < kWorkBuckets ? cells_max_occupancy : kWorkBuckets;
+		const int m2 = cells_mid_occupancy < m1 ? m1 : (cells_mid_occupancy < kWorkBuckets ? cells_mid_occupancy : kWorkBuckets);
+		const int split2 = s[c * kWorkBuckets + (kWorkBuckets - m2)], split1 = s[c * kWorkBuckets + (kWorkBuckets - m1)];
+		ranges[6 * c + 0] = s[c * kWorkBuckets];
+		ranges[6 * c + 1] = split2;
+		ranges[6 * c + 2] = split2;
+		ranges[6 * c + 3] = split1;
+		ranges[6 * c + 4] = split1;
+		ranges[6 * c + 5] = s[(c + 1) * kWorkBuckets];
 	}
 }
 
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int
 
 // ---------------------------------------------------------------------------------------------
 int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, int cells_max_occupancy,
-		cudaStream_t st) {
+		int cells_mid_occupancy, cudaStream_t st) {
 	const int N = sc.N;
 	const int nc = sc.n_cells + 1; // + the trash cell that collects particles outside the held layers
 	cudaMemsetAsync(cb.bins, 0, sizeof(int) * kBinInts, st);
@@ -265,7 +269,7 @@ int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView
 	k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_start, cb.tile_sums, nc);
 	k_cell_scatter<<<nb, 256, 0, st>>>(N, cb.cell_of, cb.cell_start, cb.cell_fill, cb.perm);
 	k_cell_order<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.perm, src.pid, cb.bins + kBinCount, cb.cell_fill, cells_max_occupancy, kCellsNbCap);
-	k_bins_scan<<<1, 160, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkRanges, cells_max_occupancy);
+	k_bins_scan<<<1, 160, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkRanges, cells_max_occupancy, cells_mid_occupancy);
 	k_work_scatter<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.bins + kBinStart, cb.bins + kBinFill, cb.cell_fill, cb.work);
 	k_cell_gather_pos<<<nb, 256, 0, st>>>(sc, cb.perm, cb.cell_of, src.pos, src.pid, dst.pos, dst.pid, slot_of, cb.cell_sorted, cb.cell_start, cb.posf);
 	const long long n9 = 9ll * N;

@@ -64,6 +64,23 @@ struct Vec3 {
 	double x, y, z;
 };
 
+// x-slab decomposition: the thread that commits an accepted move of a particle in the engine's first (last) owned
+// layer also stores the new state into the left (right) neighbour's halo copy of that layer -- plain stores into the
+// neighbouring GPU's memory over NVLink (or into another engine's arrays on the same GPU).  Both sides hold the layer
+// in the same order (cells in y, z order, ids ascending inside a cell), so the slot offset inside the layer is shared.
+struct HaloMirror {
+	double4 *pos_l;       // left neighbour's position array; nullptr: no mirror (single engine)
+	double *ori_l;
+	uint2 *posf_l;
+	double4 *pos_r;       // right neighbour's arrays (its left halo starts at slot 0)
+	double *ori_r;
+	uint2 *posf_r;
+	const int *off_l_ptr; // where the left neighbour published the first slot of its right halo; nullptr: off_l holds it
+	int off_l;
+	int ls1, ls2, ls3;    // this engine's first owned layer is [ls1, ls2), its last owned layer starts at ls3
+	int pad;
+};
+
 // ---------------------------------------------------------------------------------------------
 // exact helpers (no contraction)
 // ---------------------------------------------------------------------------------------------
@@ -354,6 +371,39 @@ __device__ __forceinline__ int neighbour_slot(const Neighbourhood &nb, int j) {
 
 __device__ __forceinline__ double4 ld_pos(const double4 *__restrict__ pos, int slot) {
 	return pos[slot];
+}
+
+// the halo copy of an accepted move (see HaloMirror); off_l: first slot of the left neighbour's right halo
+__device__ __forceinline__ void mirror_state(const HaloMirror &hm, int off_l, int sp, const Vec3 &p, const uint2 shadow, const double *m) {
+	if(hm.pos_l == nullptr) return;
+	double4 *tp;
+	double *to;
+	uint2 *tf;
+	int d;
+	if(sp < hm.ls2) {
+		tp = hm.pos_l;
+		to = hm.ori_l;
+		tf = hm.posf_l;
+		d = off_l + (sp - hm.ls1);
+	}
+	else if(sp >= hm.ls3) {
+		tp = hm.pos_r;
+		to = hm.ori_r;
+		tf = hm.posf_r;
+		d = sp - hm.ls3;
+	}
+	else return;
+	double *q = reinterpret_cast<double *>(tp + d); // x, y, z; the id in .w stays
+	q[0] = p.x;
+	q[1] = p.y;
+	q[2] = p.z;
+	tf[d] = shadow;
+#pragma unroll
+	for(int k = 0; k < 9; k++) to[9ll * d + k] = m[k];
+}
+
+__device__ __forceinline__ int mirror_offset(const HaloMirror &hm) {
+	return (hm.pos_l != nullptr && hm.off_l_ptr != nullptr) ? __ldcg(hm.off_l_ptr) : hm.off_l;
 }
 
 } // namespace pp

@@ -18,8 +18,9 @@ constexpr int kCellsNbCap = 48; // neighbours the thread-per-cell sweep kernel c
 constexpr int kBinCount = 0;                              // [8 * kWorkBuckets] cells per bin
 constexpr int kBinStart = 8 * kWorkBuckets;               // [8 * kWorkBuckets + 1] exclusive prefix
 constexpr int kBinFill = kBinStart + 8 * kWorkBuckets + 1; // [8 * kWorkBuckets] scatter cursors
-constexpr int kWorkRanges = kBinFill + 8 * kWorkBuckets;  // [8][4] per colour: tile-kernel range {begin, end}, thread-kernel range {begin, end}
-constexpr int kBinInts = kWorkRanges + 32;
+constexpr int kWorkRanges = kBinFill + 8 * kWorkBuckets;  // [8][6] per colour: {begin, end} of the crowded cells (8 lanes per cell or the tile kernel),
+                                                          // of the middle range (4 lanes per cell) and of the sparsely populated cells (one thread per cell)
+constexpr int kBinInts = kWorkRanges + 48;
 
 struct CellBuffers {
 	int *cell_of;     // N: cell of each particle in source order
@@ -55,21 +56,27 @@ struct ProposalIO {
 
 // K1: returns the number of kernels launched.  cells_max_occupancy: cells with at most that many members go to
 // the thread-per-cell sweep kernel, the more crowded ones to the tile kernel (0: everything to the tile kernel)
+// cells_mid_occupancy >= cells_max_occupancy: cells with more members than cells_max_occupancy and at most cells_mid_occupancy form the middle range
 int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView &src, const StateView &dst, int *slot_of, int cells_max_occupancy,
-		cudaStream_t st);
+		int cells_mid_occupancy, cudaStream_t st);
 
 // K2a: proposals of all N trials of one sweep (trial t of a cell lives at index cell_start[cell] + t)
 int launch_proposals_for_sweep(const SimConst &sc, const CellBuffers &cb, Proposal *proposals, cudaStream_t st);
 // K2b: one colour pass of the checkerboard sweep over the work items [range[0], range[1]) (device-resident range):
 // tile of `lanes` threads per cell ...
 int launch_sweep_pass(const SimConst &sc, const int *range, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
-		Counters *counters, cudaStream_t st);
+		Counters *counters, const HaloMirror &hm, cudaStream_t st);
 // ... or one thread per cell (sparsely populated cells; needs at least 3 distinct cells per axis)
 int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
-		double *ori, Counters *counters, cudaStream_t st);
+		double *ori, Counters *counters, const HaloMirror &hm, cudaStream_t st);
+// ... or the three configurations side by side in one launch: ranges = {8-lane begin, end, 4-lane begin, end, 1-lane begin, end}
+int launch_sweep_fused(const SimConst &sc, const int *ranges, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
+		double *ori, Counters *counters, const HaloMirror &hm, cudaStream_t st);
 
 // K3: full bond count + overlap flag into counters->bonds / counters->overlap (zeroed by the launcher)
-int launch_total_bonds(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, Counters *counters, cudaStream_t st);
+// (posf: the shadows of the same slots; nullptr or a grid with fewer than four cells on an axis: the tile kernel without the FP32 screen)
+int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint2 *posf,
+		Counters *counters, cudaStream_t st);
 // per-particle bonded-neighbour counts (indexed by particle id)
 int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, int *neighbours,
 		int max_nb, cudaStream_t st);
@@ -80,7 +87,7 @@ int launch_rescale(int N, const double4 *src, double4 *dst, double fx, double fy
 // K5: proposal evaluator against the frozen configuration
 int launch_proposals(const SimConst &sc, int n, const ProposalIO &io, const int *cell_start, const double4 *pos, const double *ori, const int *slot_of,
 		cudaStream_t st);
-int launch_commit(int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, cudaStream_t st);
+int launch_commit(const SimConst &sc, int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, uint2 *posf, cudaStream_t st);
 
 // K6: Gram-Schmidt on every orientation matrix
 int launch_orthonormalise(int N, double *ori, cudaStream_t st);
@@ -90,18 +97,18 @@ int launch_slab_classify(const SimConst &sc_new, int slot_begin, int slot_end, i
 		double *out_left, double *out_right, int cap_records, int *counts, cudaStream_t st);
 int launch_slab_unpack(int n, const double *records, int offset, const StateView &dst, cudaStream_t st);
 int launch_slab_download(int slot_begin, int slot_end, const StateView &cur, int *ids, double *r, double *orient, cudaStream_t st);
-int launch_halo_push(const double4 *pos, const double *ori, const uint2 *posf, int n, char *peer_mbox, long long cap, unsigned long long *peer_flag,
-		unsigned long long epoch, unsigned int *done, cudaStream_t st);
+// phase numbers between neighbouring engines: release store into the neighbours' control words / acquire spin on one's own
+int launch_phase_signal(unsigned long long *peer_a, unsigned long long *peer_b, unsigned long long value, int *layout_dst, int layout_val, const int *status,
+		cudaStream_t st);
+int launch_phase_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long need, int *status, cudaStream_t st);
 int launch_records_push(const double *outbox, const int *counts, int which, int cap, double *peer_box, int *peer_count, unsigned long long *peer_flag,
 		unsigned long long epoch, unsigned int *done, cudaStream_t st);
 int launch_records_pull(const double *mbox, const int *my_count, const unsigned long long *flag, unsigned long long epoch, int cap, double *inbox,
 		int *in_count, int *status, cudaStream_t st);
 int launch_gather_ints(const int *src, const int *idx, int n, int *out, cudaStream_t st);
-int launch_halo_pull(const char *mbox, long long cap, const unsigned long long *flag, unsigned long long epoch, double4 *pos, double *ori, uint2 *posf,
-		int n, int *status, cudaStream_t st);
 
 // upload / download helpers (caller order <-> slot order)
-int launch_pack_state(int N, const double *r, const double *orient, double4 *pos, double *ori, int *pid, cudaStream_t st);
+int launch_pack_state(int N, const double *r, const double *orient, const int *ids, double4 *pos, double *ori, int *pid, cudaStream_t st);
 int launch_unpack_state(int N, const double4 *pos, const double *ori, const int *pid, double *r, double *orient, cudaStream_t st);
 
 } // namespace pp

@@ -13,13 +13,10 @@
 //   k_slab_download  compacts the owned particles for output.
 // A record is 13 doubles: x, y, z, id, orientation[9].
 //
-// In-period halo refresh over peer memory (all engines on one NVLink / NVSwitch node): every engine
-// owns two mailboxes that its neighbours map with CUDA IPC.
-//   k_halo_push  copies a boundary layer (positions, orientations, shadows) straight into the
-//                neighbour's mailbox with NVLink stores; the last block to finish publishes the
-//                refresh number in the neighbour's flag (release, system scope);
-//   k_halo_pull  waits for that flag (acquire, system scope) and moves the mailbox into the halo
-//                layer.  No host synchronisation, no collective library call on the sweep path.
+// In-period halo refresh: none.  The sweep kernels mirror every accepted move of a boundary-layer particle into the
+// neighbour's halo copy themselves (HaloMirror, pp_common.cuh); neighbouring engines only exchange phase numbers
+// (k_phase_signal / k_phase_wait below).  Migration records travel through mailboxes in the neighbour's memory
+// (k_records_push / k_records_pull).
 #include "pp_kernels.cuh"
 
 namespace pp {
@@ -105,55 +102,42 @@ __global__ void __launch_bounds__(256) k_slab_download(int slot_begin, int slot_
 	for(int k = 0; k < 9; k++) orient[9ll * i + k] = ori[9ll * s + k];
 }
 
-__global__ void __launch_bounds__(256) k_halo_push(const double4 *__restrict__ pos, const double *__restrict__ ori, const uint2 *__restrict__ posf, int n,
-		char *mbox /* peer memory */, long long cap, unsigned long long *flag /* peer memory */, unsigned long long epoch, unsigned int *done) {
-	double2 *mp = reinterpret_cast<double2 *>(mbox);
-	double *mo = reinterpret_cast<double *>(mbox + 32ll * cap);
-	uint2 *mf = reinterpret_cast<uint2 *>(mbox + 104ll * cap);
-	const double2 *p2 = reinterpret_cast<const double2 *>(pos);
-	const long long stride = (long long) gridDim.x * blockDim.x, i0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	for(long long i = i0; i < 2ll * n; i += stride) mp[i] = p2[i];
-	for(long long i = i0; i < n; i += stride) mf[i] = posf[i];
-	for(long long i = i0; i < 9ll * n; i += stride) mo[i] = ori[i];
-	__threadfence_system();
-	__syncthreads();
-	if(threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) { // every block's stores are out: publish
-		*done = 0;
-		__threadfence_system();
-		asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
-	}
-}
-
 __device__ __forceinline__ unsigned long long global_timer_ns() {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
 
-__global__ void __launch_bounds__(256) k_halo_pull(const char *__restrict__ mbox, long long cap, const unsigned long long *flag, unsigned long long epoch,
-		double4 *__restrict__ pos, double *__restrict__ ori, uint2 *__restrict__ posf, int n, int *status) {
-	if(threadIdx.x == 0) {
-		const unsigned long long t0 = global_timer_ns();
+// Phase numbers between neighbouring engines.  After a rebuild, a block of four colour passes or a box move an engine
+// stores the number of phases it has completed into the control words of both neighbours (release, system scope; the
+// kernels before it on the stream, with their stores into the neighbour's halo, are complete).  Before a phase that
+// reads what a neighbour wrote, or writes where a neighbour may still read, a one-thread kernel spins on the engine's
+// own control word (acquire) until the neighbour has completed as many phases as the engine itself.
+__global__ void k_phase_signal(unsigned long long *peer_a, unsigned long long *peer_b, unsigned long long value, int *layout_dst, int layout_val,
+		const int *status) {
+	if(*status) return; // a wait timed out earlier: do not let the neighbours run on
+	if(layout_dst) *layout_dst = layout_val; // first slot of this engine's right halo, for the right neighbour's mirror stores
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_a), "l"(value) : "memory");
+	if(peer_b != peer_a) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_b), "l"(value) : "memory");
+}
+
+__global__ void k_phase_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long need, int *status) {
+	const unsigned long long t0 = global_timer_ns();
+	for(int k = 0; k < 2; k++) {
+		const unsigned long long *flag = k == 0 ? flag_a : flag_b;
+		if(flag == nullptr) continue;
 		for(;;) {
 			unsigned long long v;
 			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-			if(v >= epoch) break;
+			if(v >= need) break;
 			if(global_timer_ns() - t0 > 20000000000ull) { // 20 s: the neighbour is gone; report instead of hanging
 				atomicExch(status, 1);
-				break;
+				return;
 			}
-			__nanosleep(200);
+			__nanosleep(100);
 		}
 	}
-	__syncthreads();
-	const double2 *mp = reinterpret_cast<const double2 *>(mbox);
-	const double *mo = reinterpret_cast<const double *>(mbox + 32ll * cap);
-	const uint2 *mf = reinterpret_cast<const uint2 *>(mbox + 104ll * cap);
-	double2 *p2 = reinterpret_cast<double2 *>(pos);
-	const long long stride = (long long) gridDim.x * blockDim.x, i0 = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-	for(long long i = i0; i < 2ll * n; i += stride) p2[i] = __ldcg(mp + i);
-	for(long long i = i0; i < n; i += stride) posf[i] = __ldcg(mf + i);
-	for(long long i = i0; i < 9ll * n; i += stride) ori[i] = __ldcg(mo + i);
 }
 
 // migration records at a grid shift, over the same peer mailboxes: the sender's count travels with the data
@@ -222,19 +206,14 @@ int launch_records_pull(const double *mbox, const int *my_count, const unsigned 
 	return 1;
 }
 
-int launch_halo_push(const double4 *pos, const double *ori, const uint2 *posf, int n, char *peer_mbox, long long cap, unsigned long long *peer_flag,
-		unsigned long long epoch, unsigned int *done, cudaStream_t st) {
-	int blocks = (9 * n + 255) / 256;
-	blocks = blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks);
-	k_halo_push<<<blocks, 256, 0, st>>>(pos, ori, posf, n, peer_mbox, cap, peer_flag, epoch, done);
+int launch_phase_signal(unsigned long long *peer_a, unsigned long long *peer_b, unsigned long long value, int *layout_dst, int layout_val, const int *status,
+		cudaStream_t st) {
+	k_phase_signal<<<1, 1, 0, st>>>(peer_a, peer_b, value, layout_dst, layout_val, status);
 	return 1;
 }
 
-int launch_halo_pull(const char *mbox, long long cap, const unsigned long long *flag, unsigned long long epoch, double4 *pos, double *ori, uint2 *posf,
-		int n, int *status, cudaStream_t st) {
-	int blocks = (9 * n + 255) / 256;
-	blocks = blocks < 1 ? 1 : (blocks > 592 ? 592 : blocks);
-	k_halo_pull<<<blocks, 256, 0, st>>>(mbox, cap, flag, epoch, pos, ori, posf, n, status);
+int launch_phase_wait(const unsigned long long *flag_a, const unsigned long long *flag_b, unsigned long long need, int *status, cudaStream_t st) {
+	k_phase_wait<<<1, 1, 0, st>>>(flag_a, flag_b, need, status);
 	return 1;
 }
 

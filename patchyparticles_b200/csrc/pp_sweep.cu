@@ -129,7 +129,7 @@ __host__ __device__ constexpr int sweep_threads() {
 template<int G>
 __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) k_sweep_pass(const __grid_constant__ SimConst sc, const int *__restrict__ range,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals,
-		double4 *pos, double *ori, uint2 *posf, Counters *__restrict__ counters) {
+		double4 *pos, double *ori, uint2 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
 	constexpr int kThreads = sweep_threads<G>();
 	constexpr int kTiles = kThreads / G;
 	__shared__ TileSmem<G> s_tile[kTiles];
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 
 	const int w_begin = range[0], w_end = range[1];
 	const int nyz = sc.n_side[1] * sc.n_side[2];
+	const int hm_off = mirror_offset(hm);
 	// per-tile tallies (kept by every lane, flushed by lane 0)
 	unsigned int a_tries = 0, a_acc = 0, a_conf = 0, a_ovl = 0;
 	unsigned long long a_wt = 0, a_wa = 0, a_checks = 0;
@@ -299,7 +300,9 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 					p[0] = p_new.x;
 					p[1] = p_new.y;
 					p[2] = p_new.z;
-					posf[sp] = cell_shadow(sc, p_new.x, p_new.y, p_new.z, pick);
+					const uint2 moved = cell_shadow(sc, p_new.x, p_new.y, p_new.z, pick);
+					posf[sp] = moved;
+					mirror_state(hm, hm_off, sp, p_new, moved, ts.m_new);
 					if(staged) {
 						ts.x[j_self] = p_new.x;
 						ts.y[j_self] = p_new.y;
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 
 template<int G>
 static int launch_pass_g(const SimConst &sc, const int *range, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori, Counters *counters,
-		cudaStream_t st) {
+		const HaloMirror &hm, cudaStream_t st) {
 	constexpr int kThreads = sweep_threads<G>();
 	// the number of non-empty cells of this colour lives on the device (work_start); size the grid for
 	// the worst case (every active cell occupied, at most one cell per particle) and let surplus tiles exit
@@ -350,21 +353,21 @@ static int launch_pass_g(const SimConst &sc, const int *range, const CellBuffers
 	const long long cap = 148ll * 8 * 3; // three waves of resident blocks; tiles stride over the occupancy-sorted list
 	if(blocks > cap) blocks = cap;
 	if(blocks < 1) blocks = 1;
-	k_sweep_pass<G><<<(unsigned) blocks, kThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters);
+	k_sweep_pass<G><<<(unsigned) blocks, kThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters, hm);
 	return 1;
 }
 
 int launch_sweep_pass(const SimConst &sc, const int *range, int lanes, const CellBuffers &cb, const Proposal *proposals, double4 *pos, double *ori,
-		Counters *counters, cudaStream_t st) {
+		Counters *counters, const HaloMirror &hm, cudaStream_t st) {
 	switch(lanes) {
 	case 4:
-		return launch_pass_g<4>(sc, range, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<4>(sc, range, cb, proposals, pos, ori, counters, hm, st);
 	case 8:
-		return launch_pass_g<8>(sc, range, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<8>(sc, range, cb, proposals, pos, ori, counters, hm, st);
 	case 16:
-		return launch_pass_g<16>(sc, range, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<16>(sc, range, cb, proposals, pos, ori, counters, hm, st);
 	default:
-		return launch_pass_g<32>(sc, range, cb, proposals, pos, ori, counters, st);
+		return launch_pass_g<32>(sc, range, cb, proposals, pos, ori, counters, hm, st);
 	}
 }
 

@@ -77,11 +77,23 @@ __host__ __device__ constexpr int lane_cap(int G) { return G == 1 ? kCellsNbCap 
 
 // Latency configuration (G >= 4): the proposals of the cell's trials and the FP64 state of its own particles are
 // staged too, so that a trial of a crowded cell does not wait for global memory between its steps.
-constexpr int kMaxOwn = 8;
+__host__ __device__ constexpr int max_own(int G) { return G >= 8 ? 8 : 4; }
+template<int kMaxOwn>
 struct OwnStage {
 	Proposal pr[kMaxOwn];
 	double4 pos[kMaxOwn];
 	double ori[kMaxOwn * 9];
+};
+
+// shared memory of one block (64 threads) running G lanes per cell
+template<int G>
+struct CellSmem {
+	uint2 stage[lane_cap(G)][kCellThreads];        // [entry][thread]: shadow of a staged neighbour
+	unsigned char tag[lane_cap(G)][kCellThreads];  // its neighbour-cell code, 0 .. 26
+	unsigned char cand[lane_cap(G)][kCellThreads];
+	float4 off[28];                                // offset of neighbour cell `code` from the home cell, minus 2^23 shadow units
+	CellBlockCounters cnt;
+	OwnStage<max_own(G)> own[G >= 4 ? kCellThreads / G : 1];
 };
 
 // G lanes per cell.  Lane l stages and screens the columns c = l, l + G, ... of the 3 x 3 columns of the
@@ -90,23 +102,25 @@ struct OwnStage {
 // the throughput configuration; G > 1 shortens the serial chain of a cell when a pass is too small to
 // fill the machine.
 template<int G>
-__global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
-		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
-		uint2 *posf, Counters *__restrict__ counters) {
+__device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst &sc, const int w_begin, const int w_end, const int block, const int n_blocks,
+		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori, uint2 *posf,
+		Counters *__restrict__ counters, const HaloMirror &hm) {
 	constexpr int kCap = lane_cap(G);
 	constexpr bool kOwn = G >= 4;
+	constexpr int kMaxOwn = max_own(G);
 	constexpr int kGroups = kCellThreads / G;
 	constexpr int kOwner = 4 % G; // the lane that stages the home column (c = 4) holds the moved particle's entry and does the book-keeping
-	__shared__ __align__(8) uint2 s_stage[kCap][kCellThreads]; // [entry][thread]: shadow of a staged neighbour
-	__shared__ unsigned char s_tag[kCap][kCellThreads];       // its neighbour-cell code, 0 .. 26
-	__shared__ unsigned char s_cand[kCap][kCellThreads];
-	__shared__ __align__(16) float4 s_off[28]; // offset of neighbour cell `code` from the home cell, minus 2^23 shadow units
-	__shared__ CellBlockCounters s_cnt;
-	__shared__ __align__(16) OwnStage s_own[kOwn ? kGroups : 1];
+	uint2 (&s_stage)[kCap][kCellThreads] = sm.stage;
+	unsigned char (&s_tag)[kCap][kCellThreads] = sm.tag;
+	unsigned char (&s_cand)[kCap][kCellThreads] = sm.cand;
+	float4 (&s_off)[28] = sm.off;
+	CellBlockCounters &s_cnt = sm.cnt;
+	OwnStage<kMaxOwn> *s_own = sm.own;
 	const int tid = threadIdx.x;
-	if((long long) blockIdx.x * kGroups >= range[1] - range[0]) return; // the grid is sized for the worst case: nothing left for this block
+	if((long long) block * kGroups >= w_end - w_begin) return; // the grid is sized for the worst case: nothing left for this block
+	const int hm_off = mirror_offset(hm);
 	const int gl = tid & (G - 1); // lane inside the group
-	OwnStage &os = s_own[kOwn ? tid / G : 0];
+	OwnStage<kMaxOwn> &os = s_own[kOwn ? tid / G : 0];
 	const unsigned gmask = (G == 1) ? 0u : (((1u << G) - 1u) << ((tid & 31) & ~(G - 1)));
 	const int owner_lane = ((tid & 31) & ~(G - 1)) + kOwner; // warp lane of the group's owner
 	const bool is_owner = gl == kOwner;
@@ -120,7 +134,6 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 	}
 	__syncthreads();
 
-	const int w_begin = range[0], w_end = range[1];
 	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
 	const float thr = (float) sc.sqr_rcut + kScreenBand;
 	const float core_lo = 1.f - kScreenBand, core_hi = 1.f + kScreenBand; // certain overlap below, certain clearance above
@@ -128,7 +141,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 	const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - kScreenBand) : -1.f;
 	Tally tl = {0, 0, 0, 0, 0, 0, 0, 0};
 
-	for(int wi = w_begin + blockIdx.x * kGroups + tid / G; wi < w_end; wi += gridDim.x * kGroups) {
+	for(int wi = w_begin + block * kGroups + tid / G; wi < w_end; wi += n_blocks * kGroups) {
 		const int cell = work[wi];
 		const int ix = cell / nyz, iy = (cell - ix * nyz) / nz, iz = cell - ix * nyz - iy * nz;
 		const int first = cell_start[cell];
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 			const double *own_ori = own_staged ? os.ori + 9 * pick : ori + 9ll * sp;
 			if(is_owner) tl.tries++;
 			if(!staged) { // neighbourhood larger than the staging area (dense packing): serial FP64 path
-				if(is_owner) trial_serial(sc, cell_start, pos, ori, posf, proposals + first + t, cell, ix, iy, iz, sp, tl);
+				if(is_owner) trial_serial(sc, cell_start, pos, ori, posf, proposals + first + t, cell, ix, iy, iz, sp, tl, hm, hm_off);
 				continue;
 			}
 			const double dx = pr->dx, dy = pr->dy, dz = pr->dz;
@@ -320,6 +333,7 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 				s_stage[j_self][tid] = moved;
 #pragma unroll
 				for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
+				mirror_state(hm, hm_off, sp, p_new, moved, mn);
 				if(own_staged) {
 					os.pos[pick] = make_double4(p_new.x, p_new.y, p_new.z, p4.w);
 #pragma unroll
@@ -368,26 +382,78 @@ __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_co
 	}
 }
 
+// one configuration alone over one range of the work list
+template<int G>
+__global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
+		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
+		uint2 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
+	__shared__ __align__(16) CellSmem<G> sm;
+	sweep_cells_body<G>(sm, sc, range[0], range[1], (int) blockIdx.x, (int) gridDim.x, cell_start, work, proposals, pos, ori, posf, counters, hm);
+}
+
+// One launch per colour pass: the three ranges of the colour's work list (occupancy descending) run side by side in one
+// grid -- the most crowded cells on 8 lanes per cell, the middle range on 4, the sparsely populated rest on one thread
+// per cell.  The first blocks take the crowded cells (the longest serial chains start first); each configuration gets
+// the blocks its range needs, capped by its share of the grid, and strides over its range.
+union FusedSmem {
+	CellSmem<1> c1;
+	CellSmem<4> c4;
+	CellSmem<8> c8;
+	__device__ FusedSmem() {}
+};
+
+__global__ void __launch_bounds__(kCellThreads, 6) k_sweep_fused(const __grid_constant__ SimConst sc, const int *__restrict__ ranges /* 6 ints */,
+		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
+		uint2 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
+	__shared__ __align__(16) unsigned char raw[sizeof(FusedSmem)];
+	const int b8 = ranges[0], e8 = ranges[1], b4 = ranges[2], e4 = ranges[3], b1 = ranges[4], e1 = ranges[5];
+	const int grid = (int) gridDim.x;
+	int n8 = (e8 - b8 + 7) / 8, n4 = (e4 - b4 + 15) / 16, n1 = (e1 - b1 + 63) / 64;
+	// shares of a grid that is smaller than the work: crowded cells keep at most a quarter each, the rest goes to the sparse range
+	n8 = min(n8, max(grid / 4, 1));
+	n4 = min(n4, max(grid / 4, 1));
+	n1 = min(n1, max(grid - n8 - n4, 1));
+	const int b = (int) blockIdx.x;
+	if(b < n8) sweep_cells_body<8>(*reinterpret_cast<CellSmem<8> *>(raw), sc, b8, e8, b, n8, cell_start, work, proposals, pos, ori, posf, counters, hm);
+	else if(b < n8 + n4)
+		sweep_cells_body<4>(*reinterpret_cast<CellSmem<4> *>(raw), sc, b4, e4, b - n8, n4, cell_start, work, proposals, pos, ori, posf, counters, hm);
+	else if(b < n8 + n4 + n1)
+		sweep_cells_body<1>(*reinterpret_cast<CellSmem<1> *>(raw), sc, b1, e1, b - n8 - n4, n1, cell_start, work, proposals, pos, ori, posf, counters, hm);
+}
+
 template<int G>
 static void launch_cells_g(const SimConst &sc, const int *range, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
-		double *ori, Counters *counters, cudaStream_t st) {
+		double *ori, Counters *counters, const HaloMirror &hm, cudaStream_t st) {
 	constexpr int groups = kCellThreads / G;
 	long long blocks = (max_items + groups - 1) / groups;
 	const long long cap = 148ll * 4 * 8; // a few waves of resident blocks; groups stride over the occupancy-sorted list
 	if(blocks > cap) blocks = cap;
-	k_sweep_cells<G><<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters);
+	k_sweep_cells<G><<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, range, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters, hm);
 }
 
 // range: device pointer to {first work item, one past the last work item}; lanes: 1, 2, 4 or 8 lanes per cell
 int launch_sweep_cells(const SimConst &sc, const int *range, long long max_items, int lanes, const CellBuffers &cb, const Proposal *proposals,
-		double4 *pos, double *ori, Counters *counters, cudaStream_t st) {
+		double4 *pos, double *ori, Counters *counters, const HaloMirror &hm, cudaStream_t st) {
 	if(max_items < 1) max_items = 1;
 	switch(lanes) {
-	case 8: launch_cells_g<8>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
-	case 4: launch_cells_g<4>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
-	case 2: launch_cells_g<2>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
-	default: launch_cells_g<1>(sc, range, max_items, cb, proposals, pos, ori, counters, st); break;
+	case 8: launch_cells_g<8>(sc, range, max_items, cb, proposals, pos, ori, counters, hm, st); break;
+	case 4: launch_cells_g<4>(sc, range, max_items, cb, proposals, pos, ori, counters, hm, st); break;
+	case 2: launch_cells_g<2>(sc, range, max_items, cb, proposals, pos, ori, counters, hm, st); break;
+	default: launch_cells_g<1>(sc, range, max_items, cb, proposals, pos, ori, counters, hm, st); break;
 	}
+	return 1;
+}
+
+// ranges: device pointer to the colour's six range bounds {8-lane begin, end, 4-lane begin, end, 1-lane begin, end}
+int launch_sweep_fused(const SimConst &sc, const int *ranges, long long max_items, const CellBuffers &cb, const Proposal *proposals, double4 *pos,
+		double *ori, Counters *counters, const HaloMirror &hm, cudaStream_t st) {
+	if(max_items < 1) max_items = 1;
+	// worst case: every active cell non-empty and sparse needs max_items / 64 blocks, every one crowded max_items / 8;
+	// typical fluids need about max_items / 40.  The kernel strides when the grid is smaller than the work.
+	long long blocks = (max_items + 15) / 16 + 8;
+	const long long cap = 148ll * 6 * 6;
+	if(blocks > cap) blocks = cap;
+	k_sweep_fused<<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, ranges, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters, hm);
 	return 1;
 }
 

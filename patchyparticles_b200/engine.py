@@ -29,7 +29,7 @@ class Params(C.Structure):
                 ("Lx_change_max", C.c_double), ("Lyz_min", C.c_double), ("Lyz_max", C.c_double),
                 ("Lx_reference_sign", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
                 ("lanes_per_cell", C.c_int), ("cell_lanes", C.c_int), ("cells_max_occupancy", C.c_int),
-                ("shift_every", C.c_int)]
+                ("shift_every", C.c_int), ("cells_mid_occupancy", C.c_int)]
 
 
 class Observables(C.Structure):
@@ -38,7 +38,7 @@ class Observables(C.Structure):
                 ("tries", C.c_longlong * N_MOVES), ("accepted", C.c_longlong * N_MOVES),
                 ("confined", C.c_longlong), ("overlapped", C.c_longlong), ("acceptance_roto", C.c_double),
                 ("pair_checks", C.c_longlong), ("n_side", C.c_int * 3),
-                ("volume", C.c_double)]
+                ("volume", C.c_double), ("w_tries", C.c_ulonglong), ("w_accepted", C.c_ulonglong)]
 
 
 def library_path():
@@ -56,7 +56,18 @@ ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy",
                "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats", "pp_slab_setup", "pp_slab_range",
                "pp_slab_sweep_begin", "pp_slab_outbox", "pp_slab_inbox", "pp_slab_sweep_rebuild", "pp_slab_pass_block",
                "pp_slab_halo", "pp_slab_sweep_end", "pp_slab_download", "pp_slab_peer_export", "pp_slab_peer_connect",
-               "pp_slab_refresh", "pp_slab_peer_close", "pp_slab_sweeps", "pp_slab_migrate"]
+               "pp_slab_peer_close", "pp_slab_sweeps", "pp_slab_migrate", "pp_upload_subset", "pp_slab_select",
+               "pp_slab_box_trial", "pp_slab_box_finish", "pp_group_create", "pp_group_destroy", "pp_group_last_error",
+               "pp_group_upload", "pp_group_download", "pp_group_total_bonds", "pp_group_bond_lists", "pp_group_sweep",
+               "pp_group_sync", "pp_group_get_observables", "pp_group_check_energy", "pp_group_volume_move",
+               "pp_group_Lx_move", "pp_group_engine"]
+
+
+class PeerInfo(C.Structure):
+    """pp_peer_info: one engine's device state as a neighbour in another process maps it (CUDA IPC handle + offsets)."""
+    _fields_ = [("ipc", C.c_ubyte * 64), ("off_pos", C.c_ulonglong * 3), ("off_ori", C.c_ulonglong * 2),
+                ("off_posf", C.c_ulonglong), ("off_mig", C.c_ulonglong * 2), ("off_ctrl", C.c_ulonglong),
+                ("cap_records", C.c_longlong)]
 
 
 def load_library():
@@ -102,10 +113,30 @@ def load_library():
     L.pp_slab_pass_block.argtypes = [H, C.c_int]
     L.pp_slab_halo.argtypes = [H, C.c_int, C.c_int, PV, PV, PV, PI]
     L.pp_slab_sweep_end.argtypes = [H]
-    L.pp_slab_peer_export.argtypes = [H, C.c_char_p]
-    L.pp_slab_peer_connect.argtypes = [H, C.c_char_p, C.c_char_p]
-    L.pp_slab_refresh.argtypes = [H, C.c_int]
+    L.pp_slab_peer_export.argtypes = [H, C.POINTER(PeerInfo)]
+    L.pp_slab_peer_connect.argtypes = [H, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]
     L.pp_slab_peer_close.argtypes = [H]
+    L.pp_upload_subset.argtypes = [H, C.c_int, C.c_int, _ip, _dp, _dp, _dp]
+    L.pp_slab_select.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, _dp, _dp,
+                                 np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]
+    L.pp_slab_box_trial.argtypes = [H, C.c_int, _dp, C.c_longlong, C.POINTER(C.c_longlong), PI, PI]
+    L.pp_slab_box_finish.argtypes = [H, C.c_longlong, C.c_int, PI]
+    G = C.c_void_p
+    L.pp_group_create.argtypes = [C.POINTER(Params), C.c_int, _ip, C.POINTER(G)]
+    L.pp_group_destroy.argtypes = [G]
+    L.pp_group_last_error.argtypes = [G]
+    L.pp_group_last_error.restype = C.c_char_p
+    L.pp_group_upload.argtypes = [G, C.c_int, _dp, _dp, _dp]
+    L.pp_group_download.argtypes = [G, _dp, _dp]
+    L.pp_group_total_bonds.argtypes = [G, C.POINTER(C.c_longlong), PI]
+    L.pp_group_bond_lists.argtypes = [G, C.c_int, _ip, _ip]
+    L.pp_group_sweep.argtypes = [G, C.c_longlong]
+    L.pp_group_sync.argtypes = [G]
+    L.pp_group_get_observables.argtypes = [G, C.POINTER(Observables), C.c_int]
+    L.pp_group_check_energy.argtypes = [G, C.POINTER(C.c_longlong), PI, PI]
+    L.pp_group_volume_move.argtypes = [G, C.c_double, C.c_double, C.c_double, PI]
+    L.pp_group_Lx_move.argtypes = [G, C.c_double, C.c_double, PI]
+    L.pp_group_engine.argtypes = [G, C.c_int, C.POINTER(H)]
     L.pp_slab_sweeps.argtypes = [H, C.c_int, PI]
     L.pp_slab_migrate.argtypes = [H, PI]
     L.pp_slab_download.argtypes = [H, PI, _ip, _dp, _dp]
@@ -123,7 +154,7 @@ class Engine:
     def __init__(self, ensemble=NVT, temperature=0.1, disp_max=0.1, theta_max=0.1, kf_delta=0.119, kf_cosmax=0.98,
                  P=0.0, rescale_factor_max=0.0, Lx_move=0, Lx_change_max=0.0, Lyz_min=0.0, Lyz_max=0.0,
                  Lx_reference_sign=1, seed=12345, device=0, lanes_per_cell=0, cell_lanes=0, shift_every=0,
-                 cells_max_occupancy=-1):
+                 cells_max_occupancy=-1, cells_mid_occupancy=-1):
         self.L = load_library()
         p = Params()
         self.L.pp_default_params(C.byref(p))
@@ -133,6 +164,7 @@ class Engine:
         p.Lx_reference_sign, p.seed, p.device = Lx_reference_sign, seed, device
         p.lanes_per_cell, p.cell_lanes, p.shift_every = lanes_per_cell, cell_lanes, shift_every
         p.cells_max_occupancy = cells_max_occupancy
+        p.cells_mid_occupancy = cells_mid_occupancy
         self.params = p
         self.h = C.c_void_p()
         rc = self.L.pp_create(C.byref(p), C.byref(self.h))
@@ -274,19 +306,49 @@ class Engine:
         self._check(self.L.pp_slab_sweep_end(self.h))
 
     def slab_peer_export(self):
-        """-> the 64-byte CUDA IPC handle of this engine's halo mailboxes"""
-        buf = C.create_string_buffer(64)
-        self._check(self.L.pp_slab_peer_export(self.h, buf))
-        return buf.raw
+        """-> pp_peer_info of this engine's device state (CUDA IPC handle + offsets) as bytes"""
+        info = PeerInfo()
+        self._check(self.L.pp_slab_peer_export(self.h, C.byref(info)))
+        return bytes(info)
 
-    def slab_peer_connect(self, left_handle, right_handle):
-        self._check(self.L.pp_slab_peer_connect(self.h, left_handle, right_handle))
+    def slab_peer_connect(self, left_info, right_info):
+        l, r = PeerInfo.from_buffer_copy(left_info), PeerInfo.from_buffer_copy(right_info)
+        self._check(self.L.pp_slab_peer_connect(self.h, C.byref(l), C.byref(r)))
 
-    def slab_refresh(self, side):
-        self._check(self.L.pp_slab_refresh(self.h, int(side)))
+    def upload_subset(self, N_global, ids, box, r, orient):
+        """pp_upload_subset: the particles of the layers this slab engine holds, with their global ids"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        r = np.ascontiguousarray(r, dtype=np.float64).reshape(-1, 3)
+        orient = np.ascontiguousarray(orient, dtype=np.float64).reshape(-1, 9)
+        self.N = int(N_global)
+        n = len(ids)
+        if n == 0:
+            ids, r, orient = np.zeros(1, dtype=np.int32), np.zeros((1, 3)), np.zeros((1, 9))
+        self._check(self.L.pp_upload_subset(self.h, int(N_global), n, ids, np.ascontiguousarray(box, dtype=np.float64), r, orient))
+
+    def slab_select(self, rank, world, box, r):
+        """-> boolean mask of the particles slab `rank` of `world` has to receive (pp_slab_select)"""
+        r = np.ascontiguousarray(r, dtype=np.float64).reshape(-1, 3)
+        mine = np.zeros(max(len(r), 1), dtype=np.uint8)
+        if self.L.pp_slab_select(C.byref(self.params), rank, world, len(r), np.ascontiguousarray(box, dtype=np.float64), r, mine) != 0:
+            raise EngineError(f"the box cannot be split into {world} slabs of at least two cell layers")
+        return mine[:len(r)].astype(bool)
+
+    def slab_box_trial(self, kind, u, bonds_running_total):
+        """-> (bonds_local, overlap_local, status); see pp_slab_box_trial"""
+        b, ov, st = C.c_longlong(0), C.c_int(0), C.c_int(0)
+        uu = np.zeros(3)
+        uu[:len(u)] = u
+        self._check(self.L.pp_slab_box_trial(self.h, int(kind), uu, int(bonds_running_total), C.byref(b), C.byref(ov), C.byref(st)))
+        return int(b.value), int(ov.value), int(st.value)
+
+    def slab_box_finish(self, bonds_total, overlap_any):
+        a = C.c_int(0)
+        self._check(self.L.pp_slab_box_finish(self.h, int(bonds_total), int(overlap_any), C.byref(a)))
+        return int(a.value)
 
     def slab_sweeps(self, max_sweeps):
-        """-> sweeps done before the next grid shift (peer-memory halo refresh only)"""
+        """-> sweeps done before the next grid shift (peer connection only)"""
         done = C.c_int(0)
         self._check(self.L.pp_slab_sweeps(self.h, int(max_sweeps), C.byref(done)))
         return int(done.value)
@@ -327,3 +389,106 @@ class Engine:
 
     def reset_kernel_stats(self):
         self._check(self.L.pp_reset_kernel_stats(self.h))
+
+
+class Group:
+    """pp_group: one simulation in n x-slabs driven from this thread; devices may repeat (several slabs on one GPU).
+    Same calls as :class:`Engine`; follows the single engine's trajectory bit for bit."""
+
+    def __init__(self, n, devices=None, **params):
+        self.L = load_library()
+        p = Params()
+        self.L.pp_default_params(C.byref(p))
+        for k, v in params.items():
+            if not hasattr(p, k):
+                raise TypeError(f"unknown engine parameter {k}")
+            setattr(p, k, v)
+        self.params = p
+        self.n = int(n)
+        dev = np.ascontiguousarray(devices if devices is not None else [p.device] * self.n, dtype=np.int32)
+        self.g = C.c_void_p()
+        rc = self.L.pp_group_create(C.byref(p), self.n, dev, C.byref(self.g))
+        if rc != 0:
+            msg = self.L.pp_group_last_error(self.g).decode() if self.g else "pp_group_create failed"
+            if self.g:
+                self.L.pp_group_destroy(self.g)
+            self.g = None
+            raise EngineError(msg)
+        self.N = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.L.pp_group_last_error(self.g).decode())
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.pp_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, box, r, orient):
+        r = np.ascontiguousarray(r, dtype=np.float64).reshape(-1, 3)
+        orient = np.ascontiguousarray(orient, dtype=np.float64).reshape(-1, 9)
+        self.N = int(r.shape[0])
+        self._check(self.L.pp_group_upload(self.g, self.N, np.ascontiguousarray(box, dtype=np.float64), r, orient))
+
+    def download(self):
+        r = np.zeros((max(self.N, 1), 3))
+        m = np.zeros((max(self.N, 1), 9))
+        self._check(self.L.pp_group_download(self.g, r, m))
+        return r[:self.N], m[:self.N].reshape(-1, 3, 3)
+
+    def total_bonds(self):
+        b, ov = C.c_longlong(0), C.c_int(0)
+        self._check(self.L.pp_group_total_bonds(self.g, C.byref(b), C.byref(ov)))
+        return int(b.value), int(ov.value)
+
+    def bond_lists(self, max_per_particle=8):
+        c = np.zeros(max(self.N, 1), dtype=np.int32)
+        nb = np.full((max(self.N, 1), int(max_per_particle)), -1, dtype=np.int32)
+        self._check(self.L.pp_group_bond_lists(self.g, int(max_per_particle), c, nb.reshape(-1)))
+        return c[:self.N], nb[:self.N]
+
+    def sweep(self, nsteps=1, sync=True):
+        self._check(self.L.pp_group_sweep(self.g, int(nsteps)))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._check(self.L.pp_group_sync(self.g))
+
+    def observables(self, reset=False):
+        o = Observables()
+        self._check(self.L.pp_group_get_observables(self.g, C.byref(o), int(reset)))
+        return o
+
+    def check_energy(self):
+        b, ov, ok = C.c_longlong(0), C.c_int(0), C.c_int(0)
+        self._check(self.L.pp_group_check_energy(self.g, C.byref(b), C.byref(ov), C.byref(ok)))
+        return int(b.value), int(ov.value), bool(ok.value)
+
+    def volume_move(self, u_dir, u_vol, u_acc):
+        a = C.c_int(0)
+        self._check(self.L.pp_group_volume_move(self.g, u_dir, u_vol, u_acc, C.byref(a)))
+        return int(a.value)
+
+    def Lx_move(self, u_lx, u_acc):
+        a = C.c_int(0)
+        self._check(self.L.pp_group_Lx_move(self.g, u_lx, u_acc, C.byref(a)))
+        return int(a.value)
+
+    def slab_ranges(self):
+        """[(x0, x1, nx, n_local)] of the slabs"""
+        out = []
+        for k in range(self.n):
+            h = C.c_void_p()
+            self._check(self.L.pp_group_engine(self.g, k, C.byref(h)))
+            v = [C.c_int(0) for _ in range(4)]
+            self.L.pp_slab_range(h, *[C.byref(x) for x in v])
+            out.append(tuple(int(x.value) for x in v))
+        return out

@@ -126,27 +126,59 @@ class SlabEngine:
     def close(self):
         if self.peer_halo:
             self.eng.sync()
-            dist.barrier()  # nobody unmaps while a neighbour may still push
+            dist.barrier()  # nobody unmaps while a neighbour may still store into it
             self.eng.slab_peer_close()
             dist.barrier()
         self.eng.close()
 
+    def box_move(self, kind, u):
+        """One MC_change_volume (kind 6) / MC_change_Lx (kind 7) under the decomposition: every engine rescales and counts
+        its own layers, {bonds, overlap} are summed over the ranks (16 bytes), every engine takes the same decision.
+        -> 1 accepted, 0 rejected, -1 rejected by the Lyz window."""
+        running = self._allreduce([int(round(-self.eng.observables().energy))])[0]
+        b, ov, status = self.eng.slab_box_trial(kind, u, running)
+        if status < 0:
+            return -1 if status == -1 else 0
+        if status == 2:
+            raise NotImplementedError("a trial box that needs another cell grid re-partitions the slabs: drive this run through pp_group "
+                                      "(host/patchy_b200 with GPUs = n), which gathers and redistributes")
+        b, ov = self._allreduce([b, ov])
+        return self.eng.slab_box_finish(b, int(ov > 0))
+
     def upload(self, box, r, orient):
-        self.N = int(np.asarray(r).reshape(-1, 3).shape[0])
-        self.eng.upload(box, r, orient)  # every rank sees the whole configuration and keeps its layers
+        """Every rank is handed the whole configuration and uploads only the particles of the layers it holds (owned +
+        halo): the selection (pp_slab_select) runs on the host with the engine's own cell arithmetic."""
+        r = np.asarray(r, dtype=np.float64).reshape(-1, 3)
+        orient = np.asarray(orient, dtype=np.float64).reshape(-1, 9)
+        self.N = int(r.shape[0])
+        if self.peer_halo:
+            self.eng.sync()
+            if getattr(self, "_connected", False):
+                dist.barrier()  # nobody unmaps or frees while a neighbour may still store into it
+                self.eng.slab_peer_close()
+                dist.barrier()
+                self._connected = False
+        if hasattr(self.eng, "slab_select"):
+            mine = self.eng.slab_select(self.rank, self.world, box, r)
+            ids = np.flatnonzero(mine).astype(np.int32)
+            self.eng.upload_subset(self.N, ids, box, r[ids], orient[ids])
+        else:  # stand-in engines of the CPU tests
+            self.eng.upload(box, r, orient)
+        self.h2d_bytes = int(r[ids].nbytes + orient[ids].nbytes + ids.nbytes) if hasattr(self.eng, "slab_select") else 0
         self._halo_cache = [None, None]
         self._rebuilds = 0
         if self.peer_halo:
             self._connect_peers()
 
     def _connect_peers(self):
-        """Every engine exports its halo mailboxes (CUDA IPC) and maps those of its ring neighbours."""
+        """Every engine exports the description of its device state (CUDA IPC) and maps those of its ring neighbours."""
         mine = self.eng.slab_peer_export()
-        handles = [None] * self.world
-        dist.all_gather_object(handles, mine)
+        infos = [None] * self.world
+        dist.all_gather_object(infos, mine)
         left, right = neighbours(self.rank, self.world)
-        self.eng.slab_peer_connect(handles[left], handles[right])
-        dist.barrier()  # nobody pushes before everybody has mapped
+        self.eng.slab_peer_connect(infos[left], infos[right])
+        self._connected = True
+        dist.barrier()  # nobody stores into a neighbour before everybody has mapped
 
     def _allreduce(self, values, op=dist.ReduceOp.SUM):
         t = torch.tensor(values, dtype=torch.int64, device=self.device)
@@ -184,10 +216,7 @@ class SlabEngine:
         return send, recv
 
     def _halo_refresh(self, send_side):
-        """send_side 0: first owned layer -> left neighbour (its right halo); 1: last owned layer -> right."""
-        if self.peer_halo:
-            self.eng.slab_refresh(send_side)
-            return
+        """send / recv transport only.  send_side 0: first owned layer -> left neighbour (its right halo); 1: last owned layer -> right."""
         if self._halo_cache[send_side] is None:
             self._halo_cache[send_side] = self._halo_views(send_side)
         send, recv = self._halo_cache[send_side]
@@ -235,20 +264,15 @@ class SlabEngine:
         left = int(nsteps)
         while left > 0:
             if self.peer_halo:
+                # the data path is inside the library: accepted moves of the boundary layers are stored straight into the
+                # neighbour's halo by the sweep kernels, neighbours exchange phase numbers on the device; the driver only
+                # starts each shift period (migration) and lets the library run on until the next one
                 if e.slab_migrate():
                     self._after_rebuild()
-            elif e.slab_sweep_begin():
-                self._migrate()
-            if self.peer_halo:  # the library runs on by itself until the next grid shift
-                done = 1
-                e.slab_pass_block(0)
-                e.slab_refresh(0)
-                e.slab_pass_block(1)
-                e.slab_refresh(1)
-                e.slab_sweep_end()
-                if left > 1:
-                    done += e.slab_sweeps(left - 1)
+                done = e.slab_sweeps(left)
             else:
+                if e.slab_sweep_begin():
+                    self._migrate()
                 done = 1
                 e.slab_pass_block(0)
                 self._halo_refresh(0)

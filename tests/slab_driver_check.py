@@ -4,9 +4,9 @@ against a stand-in engine that keeps its "device" arrays in host memory.
 nccl transport: the stand-in only moves data when the driver tells it to, so after a few sweeps every halo layer must
 hold exactly what its owner last wrote -- direction, order and sizes of the halo refresh and of the migration
 exchange are checked with real messages between the ranks.
-peer transport: the data path is inside the library; the driver's job is the call sequence, which is compared with
-the one include/pp_b200.h prescribes (migrate at every grid shift, two pass blocks each followed by its refresh,
-library-side sweeps never crossing a shift)."""
+peer transport: the data path is inside the library (mirror stores from the sweep kernels, phase numbers between
+neighbours); the driver's job is the call sequence, which is compared with the one include/pp_b200.h prescribes
+(pp_slab_migrate at every grid shift, pp_slab_sweeps never crossing a shift)."""
 import os
 import sys
 
@@ -97,15 +97,15 @@ class StandInEngine:
         self.rebuilds += 1
         return True
 
-    def slab_refresh(self, side):
-        self.log.append(("refresh", self.step, side))
-
     def slab_sweeps(self, max_sweeps):
+        """like pp_slab_sweeps: refuses to start a shift period that has not been migrated, stops before the next one"""
         done = 0
-        while done < max_sweeps and self.step % PERIOD != 0:
+        while done < max_sweeps:
+            if self.step % PERIOD == 0 and getattr(self, "_migrated_at", -1) != self.step:
+                assert done > 0, "pp_slab_sweeps at the start of a shift period without pp_slab_migrate"
+                break
             for cx in (0, 1):
                 self.slab_pass_block(cx)
-                self.slab_refresh(cx)
             self.slab_sweep_end()
             done += 1
         self.log.append(("sweeps", max_sweeps, done))
@@ -137,17 +137,17 @@ def main():
     slab.sweep(3)
     slab.sweep(8)   # crosses two grid shifts, starts in the middle of a period
     assert eng.step == 11 and eng.rebuilds == 3
-    calls = [e for e in eng.log if e[0] in ("pass", "refresh", "end")]
+    calls = [e for e in eng.log if e[0] in ("pass", "end")]
     expect = []
     for s in range(11):
-        expect += [("pass", s, 0), ("refresh", s, 0), ("pass", s, 1), ("refresh", s, 1), ("end", s)]
+        expect += [("pass", s, 0), ("pass", s, 1), ("end", s)]
     assert calls == expect
     # a grid shift is never skipped: every sweep that starts a period is preceded by a successful migrate at that step
     for s in (0, 4, 8):
         i_m = eng.log.index(("migrate?", s))
         assert i_m < eng.log.index(("pass", s, 0))
     # the library-side loop never ran across a shift
-    assert all(e[2] <= PERIOD - 1 for e in eng.log if e[0] == "sweeps")
+    assert all(e[2] <= PERIOD for e in eng.log if e[0] == "sweeps")
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank} ok")

@@ -148,18 +148,19 @@ def test_bond_lists_golden(pp, oracle, name):
     e.close()
 
 
-@pytest.mark.parametrize("lanes,cell_lanes,cmo", [(0, 0, -1), (0, 1, 1), (0, 2, 2), (0, 1, 0), (1, 1, -1), (1, 2, -1), (1, 4, -1), (1, 8, -1),
-                                                  (4, 0, -1), (8, 0, -1), (16, 0, -1), (32, 0, -1), (8, 1, 3)])
-def test_sweep_matches_port(pp, oracle, lanes, cell_lanes, cmo):
+@pytest.mark.parametrize("lanes,cell_lanes,cmo,mid", [(0, 0, -1, -1), (0, 1, 1, -1), (0, 2, 2, -1), (0, 1, 0, -1), (1, 1, -1, -1), (1, 2, -1, -1),
+                                                      (1, 4, -1, -1), (1, 8, -1, -1), (4, 0, -1, -1), (8, 0, -1, -1), (16, 0, -1, -1), (32, 0, -1, -1),
+                                                      (8, 1, 3, -1), (0, 0, 1, 2), (0, 0, 1, 3), (0, 0, 2, 15), (0, 4, 1, 2)])
+def test_sweep_matches_port(pp, oracle, lanes, cell_lanes, cmo, mid):
     """The CUDA sweep and the serial restatement of the same algorithm give the same trajectory, whichever
     kernel runs it: tile kernel of any width (lanes 4..32), thread-per-cell kernel with 1..8 lanes per cell, and the
-    hybrid routing (cmo: cells with at most that many particles on the thread-per-cell kernel, the others on its
-    8-lane latency configuration or, with an explicit tile width, on the tile kernel)."""
+    fused launch (cmo / mid: cells with at most cmo particles on one thread per cell, up to mid on 4 lanes per cell, the
+    others on the 8-lane latency configuration; an explicit cell_lanes runs the three ranges as three launches)."""
     g = load_golden("gen2000_rho0.5")
     delta, cosmax, T = 0.25, 0.8, 0.15  # plenty of bonds
     port = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
     e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T, disp_max=0.2, theta_max=0.3, seed=99, lanes_per_cell=lanes, cell_lanes=cell_lanes,
-                  cells_max_occupancy=cmo)
+                  cells_max_occupancy=cmo, cells_mid_occupancy=mid)
     e.upload(g["box"], g["r"], g["orient"])
     bonds, _ = e.total_bonds()
     pb, _ = port.total_bonds()
@@ -202,15 +203,17 @@ def test_sweep_invariants_large(pp):
     e.close()
 
 
-@pytest.mark.parametrize("lanes,cell_lanes,cmo", [(0, 0, -1), (0, 1, 3), (0, 2, 1), (1, 1, -1), (1, 8, -1), (8, 0, -1)])
-def test_crystal_sweep_matches_port(pp, oracle, lanes, cell_lanes, cmo):
+@pytest.mark.parametrize("lanes,cell_lanes,cmo,mid", [(0, 0, -1, -1), (0, 1, 3, -1), (0, 2, 1, -1), (1, 1, -1, -1), (1, 8, -1, -1), (8, 0, -1, -1),
+                                                      (0, 0, 1, 2), (0, 0, 2, 3)])
+def test_crystal_sweep_matches_port(pp, oracle, lanes, cell_lanes, cmo, mid):
     """BASELINE configs[4] in small: an FCC crystal at rho = 1.041 (dofccrrr.py recipe), 41-44 particles in a 27-cell
     neighbourhood, up to 4 per cell.  Dense staging areas, crowded-cell routing and the serial fallback all follow the
     CPU restatement bit for bit."""
     box, r, m = pp.fcc_configuration(1.041, 6, 6, 6)
     T = 1.0  # warm enough for ~1000 accepted moves in 8 sweeps, with displacements large enough for ~1000 overlaps
     port = oracle.PortSystem(box, r, m, temperature=T)
-    e = pp.Engine(temperature=T, disp_max=0.15, theta_max=0.2, seed=5, lanes_per_cell=lanes, cell_lanes=cell_lanes, cells_max_occupancy=cmo)
+    e = pp.Engine(temperature=T, disp_max=0.15, theta_max=0.2, seed=5, lanes_per_cell=lanes, cell_lanes=cell_lanes, cells_max_occupancy=cmo,
+                  cells_mid_occupancy=mid)
     e.upload(box, r, m)
     pb, pov = port.total_bonds()
     assert e.total_bonds() == (pb, pov) and pov == 0 and pb > 1000
