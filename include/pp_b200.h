@@ -185,7 +185,7 @@ int pp_slab_pass_block(pp_handle *h, int cx);
 int pp_slab_halo(pp_handle *h, int side, int recv, void **pos, void **ori, void **posf, int *count);
 /* ---- the data path of the decomposition: stores into the neighbouring engine's memory, no mailbox copy -----------
  * Engines on the GPUs of one NVLink / NVSwitch node (or several engines on one GPU).  Every engine keeps its whole
- * device state in one allocation and describes it with a pp_peer_info (a CUDA IPC handle + offsets); the driver hands
+ * device state in one allocation and describes it with a pp_peer_info record, a CUDA IPC handle + offsets; the driver hands
  * each engine the descriptions of its left and right neighbour (pp_slab_peer_connect).  From then on
  *   - the sweep kernels themselves keep the neighbours' halo layers current: the thread that commits an accepted move
  *     of a particle in the engine's first (last) owned layer also stores the new position, orientation and shadow into
