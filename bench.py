@@ -237,7 +237,8 @@ class Arm:
         import torch
         N, rho, T = WORKLOADS[w]
         params = dict(temperature=T, kf_delta=KF_DELTA, kf_cosmax=KF_COSMAX, disp_max=DISP_MAX, theta_max=THETA_MAX,
-                      lanes_per_cell=args.lanes, cells_max_occupancy=args.cells_max_occupancy, cell_lanes=args.cell_lanes)
+                      lanes_per_cell=args.lanes, cells_max_occupancy=args.cells_max_occupancy, cell_lanes=args.cell_lanes,
+                      cells_mid_occupancy=args.cells_mid_occupancy)
         self.sharded = sharded
         if sharded:
             from patchyparticles_b200.slab import SlabEngine
@@ -287,6 +288,8 @@ def main():
     ap.add_argument("--cell-lanes", type=int, default=0, help="lanes per cell of the thread-per-cell kernel (0: auto, 1, 2, 4, 8)")
     ap.add_argument("--cells-max-occupancy", type=int, default=-1,
                     help="cells with at most this many particles go to the thread-per-cell kernel (-1: auto, 0: tile kernel only)")
+    ap.add_argument("--cells-mid-occupancy", type=int, default=-1,
+                    help="cells with more particles than --cells-max-occupancy and at most this many run on 4 lanes per cell (-1: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--relax-sweeps", type=int, default=300,
@@ -400,7 +403,7 @@ def main():
     # hybrid routing: two concurrent launches per colour pass (sparse cells / crowded cells), timed together
     launches_per_pass = max(1, round(sweep_launches / n_passes))
     per_launch_ms = sweep_ms / n_passes
-    sweep_kernel = "k_sweep_pass" if launches_per_pass == 1 else "k_sweep_cells<1> || k_sweep_cells<8> (the two concurrent launches of a colour pass)"
+    sweep_kernel = "k_sweep_pass (tile kernel)" if n_local < 150000 and args.cells_max_occupancy < 0 and args.lanes != 1 else "k_sweep_fused (8 / 4 / 1 lanes per cell in one launch)"
     n_owned = N / world if sharded else N
     bytes_per_launch = SWEEP_BYTES_PER_ATTEMPT * n_owned / 8.0
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9

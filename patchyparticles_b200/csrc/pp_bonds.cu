@@ -113,11 +113,18 @@ static __device__ __noinline__ void bond_pair_exact(const SimConst &sc, const do
 __global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
 		const int *__restrict__ cell_sorted, const double4 *__restrict__ pos, const double *__restrict__ ori, const uint2 *__restrict__ posf,
 		Counters *counters) {
+	// pairs that pass the FP32 screen are queued per warp and tested in FP64 by all its lanes together: the exact test is
+	// a few hundred instructions, and taken where it is found it would run with one or two lanes of the warp active
+	constexpr int kQueue = 96;
+	__shared__ int2 s_queue[kBondCellThreads / 32][kQueue];
+	__shared__ int s_queued[kBondCellThreads / 32];
 	__shared__ int s_bonds, s_overlap;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if(threadIdx.x == 0) {
 		s_bonds = 0;
 		s_overlap = 0;
 	}
+	if(lane == 0) s_queued[warp] = 0;
 	__syncthreads();
 	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
 	int bonds = 0, overlap = 0;
@@ -157,10 +164,19 @@ __global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __
 				for(int sq = sb[g]; sq < se[g]; sq++) {
 					const uint2 qh = posf[sq];
 					const float ax = fmaf(shadow16_lo(qh.x), ux, px), ay = fmaf(shadow16_hi(qh.x), uy, py), az = fmaf(shadow16_lo(qh.y), uz, oz);
-					if(fmaf(az, az, fmaf(ay, ay, ax * ax)) < thr) bond_pair_exact(sc, pos, ori, sp, sq, bonds, overlap);
+					if(fmaf(az, az, fmaf(ay, ay, ax * ax)) < thr) {
+						const int slot = atomicAdd(&s_queued[warp], 1);
+						if(slot < kQueue) s_queue[warp][slot] = make_int2(sp, sq);
+						else bond_pair_exact(sc, pos, ori, sp, sq, bonds, overlap); // (dense packings: more pairs than the queue holds)
+					}
 				}
 			}
 		}
+	}
+	__syncwarp();
+	{
+		const int n = min(s_queued[warp], kQueue);
+		for(int i = lane; i < n; i += 32) bond_pair_exact(sc, pos, ori, s_queue[warp][i].x, s_queue[warp][i].y, bonds, overlap);
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
