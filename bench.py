@@ -5,9 +5,12 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   (reference CPU arm)
 
 A "step" is one MC step of the reference (main.c:119): N_particles attempted roto-translations
-(one 8-colour checkerboard sweep including its cell build).  At 1 GPU the workload is
-BASELINE.json configs[1] (N = 65536, rho = 0.5, NVT); with more GPUs each rank runs an independent
-replica of it (weak scaling, "replicas only" -- see DESIGN.md section "multi-GPU").
+(one 8-colour checkerboard sweep including its share of the cell builds).  The workload is the same
+at every GPU count -- BASELINE.json configs[3], N = 4 194 304 at rho = 0.6, NVT -- on one engine at
+--gpus 1 and split into N x-slabs at --gpus N (strong scaling), so the driver's efficiency divides
+like by like.  The one-GPU line also carries, under "configs", the other BASELINE configurations
+measured in the same run: N = 65536 (configs[1]), the NPT run at N = 32768 (configs[2]), the FCC
+crystal at N = 256 000 (configs[4]) and N = 1000 (configs[0]).  --workload picks another one as the headline.
 
 Prints ONE JSON line on rank 0 (see the task contract): value = device-timed throughput with the
 state resident in HBM (L2 flushed between steps), e2e = the same metric through the C ABI with
@@ -38,13 +41,15 @@ WORKLOADS = {
     "1M": (1048576, 0.6, 0.1),
     "4M": (4194304, 0.6, 0.1),
 }
+DEFAULT_WORKLOAD = "4M"
+# dram__bytes_read.sum + dram__bytes_write.sum per colour-pass launch from the committed ncu captures (profiles/), by
+# (workload, GPUs); None where no capture of that shape is committed
+SWEEP_TRAFFIC = {}
 KF_DELTA, KF_COSMAX, DISP_MAX, THETA_MAX, SEED = 0.119, 0.98, 0.1, 0.1, 12345
 SWEEP_BYTES_PER_ATTEMPT = 64   # state read once + written once per sweep at S = 32 B
 CELLS_BYTES_PER_PARTICLE = 72
 BONDS_BYTES_PER_PARTICLE = 32
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-# dram__bytes_read.sum + dram__bytes_write.sum per k_sweep_pass launch from the committed ncu captures (profiles/)
-SWEEP_TRAFFIC_BYTES = {"64k": 5095520}  # profiles/r01d_sweep_full.txt (L2 flushed before each step)
 
 
 def workload_name(w):
@@ -474,7 +479,7 @@ def main():
                        "lanes_per_cell": eng.params.lanes_per_cell or "auto", "cells": arm.cells()},
             "value_l2_warm": K * attempts_per_step / (warm_ms * 1e-3),
             "wall_s_timed_region": t_wall,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": SWEEP_TRAFFIC_BYTES.get(w),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": SWEEP_TRAFFIC.get((w, world)),
                          "kernel": sweep_kernel, "peak_source": peak_src + " (of measured)",
                          "note": "algorithmic bytes = 64 B per attempted move (SURVEY 8d); traffic = ncu dram bytes per launch (profiles/); "
                                  "the sweep is latency / L2 bound, not HBM bound"},

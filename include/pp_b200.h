@@ -213,6 +213,10 @@ int pp_slab_peer_close(pp_handle *h);
  * pp_slab_select marks the particles engine `rank` of `world` has to receive for a given box (layer of each particle
  * on the unshifted grid, exactly as the engine computes it). */
 int pp_upload_subset(pp_handle *h, int N_global, int n_local, const int *ids, const double *box, const double *r, const double *orient);
+/* every engine is handed the WHOLE configuration and takes the particles of its own layers: from pinned host memory the
+ * selection and the gather run on the GPU (one kernel reading over PCIe, no host-side work, no staging copy); from
+ * pageable memory they run on the host.  Without a decomposition this is pp_upload. */
+int pp_upload_select(pp_handle *h, int N, const double *box, const double *r, const double *orient);
 int pp_slab_select(const pp_params *params, int rank, int world, int N, const double *box, const double *r, unsigned char *mine);
 /* start of a shift period: classify on the new grid, store the outgoing records into the neighbours' mailboxes, take in
  * what they stored here, rebuild the cells.  *migrated = 0 when the current period is still running. */

@@ -455,12 +455,13 @@ void sweep_shift(uint64_t seed, uint64_t epoch, const double *box, const int *n_
 	for(int k = 0; k < 3; k++) shift[k] = unit_from_u32(x[k]) * (box[k] / n_side[k]);
 }
 
-int upload_impl(pp_handle *h, int N_global, int n, const int *ids, const double *box, const double *r, const double *orient, bool keep_books) {
-	if(n < 0 || N_global < n) return fail(h, "bad particle numbers (%d local of %d)", n, N_global);
+// ---- upload ---------------------------------------------------------------------------------------------------------
+// first part of every upload: box, grid, slab partition, books
+static int upload_begin(pp_handle *h, int N_global, const double *box, bool keep_books) {
 	CUDA_OK(h, cudaSetDevice(h->device));
 	for(int k = 0; k < 3; k++)
 		if(!(box[k] > 0.)) return fail(h, "box side %d is not positive", k);
-	if(keep_books) { // fold what the device counters hold into the carry: the upload below zeroes them
+	if(keep_books) { // fold what the device counters hold into the carry: the upload zeroes them
 		if(fetch_counters(h)) return 1;
 		const Counters &c = *h->h_counters;
 		h->carry.tries += c.tries;
@@ -472,43 +473,34 @@ int upload_impl(pp_handle *h, int N_global, int n, const int *ids, const double 
 		h->carry.pair_checks += c.pair_checks;
 	}
 	else memset(&h->carry, 0, sizeof(h->carry));
-	h->N = n;
 	h->N_global = N_global;
 	memcpy(h->box, box, sizeof(h->box));
 	if(!keep_books) h->V = box[0] * box[1] * box[2];
 	if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", box[0], box[1], box[2], h->r_cut);
 	h->nxl = h->n_side[0];
-	size_t cap = (size_t) n, n_records = 0;
 	if(h->slab_world > 1) {
 		if(h->n_side[0] / 2 < h->slab_world) return fail(h, "%d x layers cannot be split over %d engines (at least 2 layers each)", h->n_side[0], h->slab_world);
 		slab_partition(h->n_side[0], h->slab_rank, h->slab_world, &h->x0, &h->x1);
 		h->nxl = (h->x1 - h->x0) + 2;
-		// records per neighbour and slack of the arrays from the fullest x layer of what this engine receives (an
-		// inhomogeneous system -- a slab of liquid, a gel -- has layers far above the mean)
-		const int nx = h->n_side[0];
-		int *layer_count = (int *) calloc((size_t) nx, sizeof(int));
-		if(layer_count == nullptr) return fail(h, "out of host memory");
-		const double inv_box = 1. / h->box[0];
-		for(int i = 0; i < n; i++) layer_count[cell_coord_host(r[3ll * i], 0., inv_box, nx)]++;
-		int fullest = 0;
-		for(int k = 0; k < nx; k++) fullest = layer_count[k] > fullest ? layer_count[k] : fullest;
-		free(layer_count);
-		n_records = 3 * (size_t) fullest + 8192;
-		cap = (size_t) n + (size_t) n / 8 + 4 * (size_t) fullest + 8192;
 		if(h->d_slab_counts == nullptr) CUDA_OK(h, cudaMalloc(&h->d_slab_counts, 16 * sizeof(int)));
 		if(h->h_slab_ints == nullptr) CUDA_OK(h, cudaMallocHost(&h->h_slab_ints, 8 * sizeof(int)));
 		h->slab_pending = false;
 	}
-	if(ensure_state(h, cap, (size_t) N_global, n_records)) return 1;
-	peer_release(h); // a new configuration: the driver connects the neighbours again
-	if(n > 0) {
-		CUDA_OK(h, cudaMemcpyAsync(h->d_stage_r, r, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, h->stream));
-		CUDA_OK(h, cudaMemcpyAsync(h->d_stage_o, orient, sizeof(double) * 9 * (size_t) n, cudaMemcpyHostToDevice, h->stream));
-		if(ids) CUDA_OK(h, cudaMemcpyAsync(h->cb.perm, ids, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, h->stream));
-	}
+	return 0;
+}
+
+// array sizes of a slab engine from the number of particles it receives and the fullest x layer among them (an
+// inhomogeneous system -- a slab of liquid, a gel -- has layers far above the mean)
+static void slab_sizes(int n, int fullest, size_t *cap, size_t *n_records) {
+	*n_records = 3 * (size_t) fullest + 8192;
+	*cap = (size_t) n + (size_t) n / 8 + 4 * (size_t) fullest + 8192;
+}
+
+// last part: the state sits unsorted in buffer 0 with n particles; reset the books, build the cells
+static int upload_finish(pp_handle *h, int n, bool check_held, bool keep_books) {
+	h->N = n;
 	h->cp = 0;
 	h->co = 0;
-	launch_pack_state(n, h->d_stage_r, h->d_stage_o, ids ? h->cb.perm : nullptr, h->pos[0], h->ori[0], h->pid[0], h->stream);
 	CUDA_OK(h, cudaMemsetAsync(h->d_counters, 0, sizeof(Counters), h->stream));
 	CUDA_OK(h, cudaMemsetAsync(h->arena + h->layout.off_ctrl, 0, 256, h->stream));
 	memset(h->h_counters, 0, sizeof(Counters));
@@ -528,9 +520,81 @@ int upload_impl(pp_handle *h, int N_global, int n, const int *ids, const double 
 	memset(&h->bm, 0, sizeof(h->bm));
 	if(ensure_cells_valid(h)) return 1;
 	CUDA_OK(h, cudaStreamSynchronize(h->stream));
-	if(h->slab_world > 1 && ids != nullptr && h->N != n)
-		return fail(h, "pp_upload_subset: %d of the %d particles lie outside the layers this engine holds", n - h->N, n);
+	if(h->slab_world > 1 && check_held && h->N != n)
+		return fail(h, "upload: %d of the %d particles lie outside the layers this engine holds", n - h->N, n);
 	return 0;
+}
+
+int upload_impl(pp_handle *h, int N_global, int n, const int *ids, const double *box, const double *r, const double *orient, bool keep_books) {
+	if(n < 0 || N_global < n) return fail(h, "bad particle numbers (%d local of %d)", n, N_global);
+	if(upload_begin(h, N_global, box, keep_books)) return 1;
+	size_t cap = (size_t) n, n_records = 0;
+	if(h->slab_world > 1) {
+		const int nx = h->n_side[0];
+		int *layer_count = (int *) calloc((size_t) nx, sizeof(int));
+		if(layer_count == nullptr) return fail(h, "out of host memory");
+		const double inv_box = 1. / h->box[0];
+		for(int i = 0; i < n; i++) layer_count[cell_coord_host(r[3ll * i], 0., inv_box, nx)]++;
+		int fullest = 0;
+		for(int k = 0; k < nx; k++) fullest = layer_count[k] > fullest ? layer_count[k] : fullest;
+		free(layer_count);
+		slab_sizes(n, fullest, &cap, &n_records);
+	}
+	if(ensure_state(h, cap, (size_t) N_global, n_records)) return 1;
+	peer_release(h); // a new configuration: the driver connects the neighbours again
+	if(n > 0) {
+		CUDA_OK(h, cudaMemcpyAsync(h->d_stage_r, r, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, h->stream));
+		CUDA_OK(h, cudaMemcpyAsync(h->d_stage_o, orient, sizeof(double) * 9 * (size_t) n, cudaMemcpyHostToDevice, h->stream));
+		if(ids) CUDA_OK(h, cudaMemcpyAsync(h->cb.perm, ids, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, h->stream));
+	}
+	launch_pack_state(n, h->d_stage_r, h->d_stage_o, ids ? h->cb.perm : nullptr, h->pos[0], h->ori[0], h->pid[0], h->stream);
+	return upload_finish(h, n, ids != nullptr, keep_books);
+}
+
+// A slab engine handed the WHOLE configuration in pinned (device-readable) host memory takes the particles of its own
+// layers itself: one kernel reads the positions over PCIe, selects by x layer with the engine's cell arithmetic, and
+// gathers positions and orientations of the selected particles straight into the device arrays -- no host-side
+// selection, no staging copy, an eighth of the orientations crosses the bus on eight engines.
+int upload_select(pp_handle *h, int N, const double *box, const double *r, const double *orient) {
+	if(upload_begin(h, N, box, false)) return 1;
+	const int nx = h->n_side[0];
+	const int lo = (h->x0 - 1 + nx) % nx, held = h->x1 - h->x0 + 2;
+	int *d_hist = nullptr; // [0] particles selected, [1] overflow, [2 .. 2 + nx) particles per global x layer
+	CUDA_OK(h, cudaMalloc(&d_hist, sizeof(int) * (size_t) (nx + 2)));
+	int *hist = (int *) malloc(sizeof(int) * (size_t) (nx + 2));
+	int rc = 0, n_sel = 0;
+	for(int attempt = 0; attempt < 2 && rc == 0; attempt++) {
+		// with arrays from an earlier upload the selection goes straight in; if they turn out too small (or there are none
+		// yet) the first pass only counts and the second one packs
+		const bool pack = h->cap_N > 0 && (size_t) N + 32 <= h->cap_ids;
+		cudaMemsetAsync(d_hist, 0, sizeof(int) * (size_t) (nx + 2), h->stream);
+		if(pack) peer_release(h);
+		launch_select_pack(N, r, orient, 1. / h->box[0], nx, lo, held, pack ? h->pos[0] : nullptr, h->ori[0], h->pid[0], (int) h->cap_N, d_hist, h->stream);
+		if(cudaMemcpyAsync(hist, d_hist, sizeof(int) * (size_t) (nx + 2), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+				cudaStreamSynchronize(h->stream) != cudaSuccess) {
+			rc = fail(h, "upload: selection kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+		n_sel = hist[0];
+		int fullest = 0;
+		for(int k = 0; k < held; k++) {
+			const int c = hist[2 + (lo + k) % nx];
+			fullest = c > fullest ? c : fullest;
+		}
+		size_t cap, n_records;
+		slab_sizes(n_sel, fullest, &cap, &n_records);
+		const bool fits = pack && !hist[1] && (size_t) n_sel + 32 <= h->cap_N && n_records <= (size_t) h->cap_records;
+		if(fits) break;
+		if(attempt == 1) {
+			rc = fail(h, "upload: the selection does not fit the arrays sized for it (%d particles)", n_sel);
+			break;
+		}
+		if(ensure_state(h, cap > h->cap_N ? cap : h->cap_N, (size_t) N, n_records > (size_t) h->cap_records ? n_records : (size_t) h->cap_records)) rc = 1;
+	}
+	free(hist);
+	cudaFree(d_hist);
+	if(rc) return rc;
+	return upload_finish(h, n_sel, true, false);
 }
 
 int sweep_once(pp_handle *h) {
@@ -827,6 +891,47 @@ int pp_upload_subset(pp_handle *h, int N_global, int n_local, const int *ids, co
 	for(int i = 0; i < n_local; i++)
 		if(ids[i] < 0 || ids[i] >= N_global) return fail(h, "pp_upload_subset: id %d out of range", ids[i]);
 	return upload_impl(h, N_global, n_local, ids, box, r, orient, false);
+}
+
+int pp_upload_select(pp_handle *h, int N, const double *box, const double *r, const double *orient) {
+	if(h == nullptr) return 1;
+	if(N < 0) return fail(h, "negative particle number");
+	if(h->slab_world <= 1) return upload_impl(h, N, N, nullptr, box, r, orient, false);
+	// can the device read the caller's arrays (pinned host memory under unified addressing)?
+	cudaPointerAttributes ar, ao;
+	const bool readable = N > 0 && cudaPointerGetAttributes(&ar, r) == cudaSuccess && cudaPointerGetAttributes(&ao, orient) == cudaSuccess &&
+			(ar.type == cudaMemoryTypeHost || ar.type == cudaMemoryTypeManaged) && (ao.type == cudaMemoryTypeHost || ao.type == cudaMemoryTypeManaged);
+	cudaGetLastError();
+	if(readable) return upload_select(h, N, box, r, orient);
+	// pageable memory: select and pack on the host
+	unsigned char *mine = (unsigned char *) malloc((size_t) N + 1);
+	if(mine == nullptr) return fail(h, "out of host memory");
+	if(pp_slab_select(&h->prm, h->slab_rank, h->slab_world, N, box, r, mine)) {
+		free(mine);
+		return fail(h, "the box (%g, %g, %g) cannot be split into %d slabs of at least two cell layers", box[0], box[1], box[2], h->slab_world);
+	}
+	size_t m = 0;
+	for(int i = 0; i < N; i++) m += mine[i];
+	int *ids = (int *) malloc(sizeof(int) * (m + 1));
+	double *rs = (double *) malloc(sizeof(double) * 3 * (m + 1)), *os = (double *) malloc(sizeof(double) * 9 * (m + 1));
+	int rc = 0;
+	if(!ids || !rs || !os) rc = fail(h, "out of host memory");
+	else {
+		size_t k = 0;
+		for(int i = 0; i < N; i++)
+			if(mine[i]) {
+				ids[k] = i;
+				memcpy(rs + 3 * k, r + 3ll * i, 3 * sizeof(double));
+				memcpy(os + 9 * k, orient + 9ll * i, 9 * sizeof(double));
+				k++;
+			}
+		rc = upload_impl(h, N, (int) m, ids, box, rs, os, false);
+	}
+	free(mine);
+	free(ids);
+	free(rs);
+	free(os);
+	return rc;
 }
 
 int pp_slab_select(const pp_params *params, int rank, int world, int N, const double *box, const double *r, unsigned char *mine) {

@@ -470,6 +470,39 @@ __global__ void __launch_bounds__(256) k_unpack_state(int N, const double4 *__re
 	for(int k = 0; k < 9; k++) orient[9ll * i + k] = ori[9ll * s + k];
 }
 
+// A slab engine takes its own particles out of the whole configuration in device-readable host memory: layer of every
+// particle with the engine's cell arithmetic (unshifted grid), per-layer histogram, and -- when pos is given -- the
+// selected particles gathered into the device arrays in arrival order (the cell build orders them by id).
+// hist: [0] selected, [1] overflow flag, [2 .. 2 + nx) particles per global layer.
+__global__ void __launch_bounds__(256) k_select_pack(int N, const double *__restrict__ r, const double *__restrict__ orient, double inv_box, int nx, int lo,
+		int held, double4 *__restrict__ pos, double *__restrict__ ori, int *__restrict__ pid, int cap, int *__restrict__ hist) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= N) return;
+	const double x = r[3ll * i];
+	const int layer = cell_coord(x, 0., inv_box, nx);
+	atomicAdd(hist + 2 + layer, 1);
+	int rel = layer - lo;
+	rel += rel < 0 ? nx : 0;
+	if(rel >= held) return;
+	const int slot = atomicAdd(hist, 1);
+	if(pos == nullptr) return;
+	if(slot >= cap) {
+		hist[1] = 1;
+		return;
+	}
+	pos[slot] = make_double4(x, r[3ll * i + 1], r[3ll * i + 2], (double) i);
+	pid[slot] = i;
+#pragma unroll
+	for(int k = 0; k < 9; k++) ori[9ll * slot + k] = orient[9ll * i + k];
+}
+
+int launch_select_pack(int N, const double *r, const double *orient, double inv_box, int nx, int lo, int held, double4 *pos, double *ori, int *pid, int cap,
+		int *hist, cudaStream_t st) {
+	if(N == 0) return 0;
+	k_select_pack<<<(N + 255) / 256, 256, 0, st>>>(N, r, orient, inv_box, nx, lo, held, pos, ori, pid, cap, hist);
+	return 1;
+}
+
 int launch_pack_state(int N, const double *r, const double *orient, const int *ids, double4 *pos, double *ori, int *pid, cudaStream_t st) {
 	if(N == 0) return 0;
 	k_pack_state<<<(N + 255) / 256, 256, 0, st>>>(N, r, orient, ids, pos, ori, pid);

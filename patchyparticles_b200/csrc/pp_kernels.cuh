@@ -108,6 +108,8 @@ int launch_records_pull(const double *mbox, const int *my_count, const unsigned 
 int launch_gather_ints(const int *src, const int *idx, int n, int *out, cudaStream_t st);
 
 // upload / download helpers (caller order <-> slot order)
+int launch_select_pack(int N, const double *r, const double *orient, double inv_box, int nx, int lo, int held, double4 *pos, double *ori, int *pid, int cap,
+		int *hist, cudaStream_t st);
 int launch_pack_state(int N, const double *r, const double *orient, const int *ids, double4 *pos, double *ori, int *pid, cudaStream_t st);
 int launch_unpack_state(int N, const double4 *pos, const double *ori, const int *pid, double *r, double *orient, cudaStream_t st);
 

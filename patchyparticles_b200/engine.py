@@ -56,7 +56,7 @@ ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy",
                "pp_set_profiling", "pp_kernel_stats", "pp_reset_kernel_stats", "pp_slab_setup", "pp_slab_range",
                "pp_slab_sweep_begin", "pp_slab_outbox", "pp_slab_inbox", "pp_slab_sweep_rebuild", "pp_slab_pass_block",
                "pp_slab_halo", "pp_slab_sweep_end", "pp_slab_download", "pp_slab_peer_export", "pp_slab_peer_connect",
-               "pp_slab_peer_close", "pp_slab_sweeps", "pp_slab_migrate", "pp_upload_subset", "pp_slab_select",
+               "pp_slab_peer_close", "pp_slab_sweeps", "pp_slab_migrate", "pp_upload_subset", "pp_upload_select", "pp_slab_select",
                "pp_slab_box_trial", "pp_slab_box_finish", "pp_group_create", "pp_group_destroy", "pp_group_last_error",
                "pp_group_upload", "pp_group_download", "pp_group_total_bonds", "pp_group_bond_lists", "pp_group_sweep",
                "pp_group_sync", "pp_group_get_observables", "pp_group_check_energy", "pp_group_volume_move",
@@ -117,6 +117,7 @@ def load_library():
     L.pp_slab_peer_connect.argtypes = [H, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]
     L.pp_slab_peer_close.argtypes = [H]
     L.pp_upload_subset.argtypes = [H, C.c_int, C.c_int, _ip, _dp, _dp, _dp]
+    L.pp_upload_select.argtypes = [H, C.c_int, _dp, _dp, _dp]
     L.pp_slab_select.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, _dp, _dp,
                                  np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")]
     L.pp_slab_box_trial.argtypes = [H, C.c_int, _dp, C.c_longlong, C.POINTER(C.c_longlong), PI, PI]
@@ -325,6 +326,16 @@ class Engine:
         if n == 0:
             ids, r, orient = np.zeros(1, dtype=np.int32), np.zeros((1, 3)), np.zeros((1, 9))
         self._check(self.L.pp_upload_subset(self.h, int(N_global), n, ids, np.ascontiguousarray(box, dtype=np.float64), r, orient))
+
+    def upload_select(self, box, r, orient):
+        """pp_upload_select: the whole configuration; a slab engine takes the particles of its own layers (on the GPU when
+        the arrays are pinned host memory)"""
+        r = np.ascontiguousarray(r, dtype=np.float64).reshape(-1, 3)
+        orient = np.ascontiguousarray(orient, dtype=np.float64).reshape(-1, 9)
+        self.N = int(r.shape[0])
+        if self.N == 0:
+            r, orient = np.zeros((1, 3)), np.zeros((1, 9))
+        self._check(self.L.pp_upload_select(self.h, self.N, np.ascontiguousarray(box, dtype=np.float64), r, orient))
 
     def slab_select(self, rank, world, box, r):
         """-> boolean mask of the particles slab `rank` of `world` has to receive (pp_slab_select)"""

@@ -146,8 +146,8 @@ class SlabEngine:
         return self.eng.slab_box_finish(b, int(ov > 0))
 
     def upload(self, box, r, orient):
-        """Every rank is handed the whole configuration and uploads only the particles of the layers it holds (owned +
-        halo): the selection (pp_slab_select) runs on the host with the engine's own cell arithmetic."""
+        """Every rank is handed the whole configuration and takes only the particles of the layers it holds (owned + halo):
+        pp_upload_select, on the GPU when the arrays are pinned host memory."""
         r = np.asarray(r, dtype=np.float64).reshape(-1, 3)
         orient = np.asarray(orient, dtype=np.float64).reshape(-1, 9)
         self.N = int(r.shape[0])
@@ -158,13 +158,12 @@ class SlabEngine:
                 self.eng.slab_peer_close()
                 dist.barrier()
                 self._connected = False
-        if hasattr(self.eng, "slab_select"):
-            mine = self.eng.slab_select(self.rank, self.world, box, r)
-            ids = np.flatnonzero(mine).astype(np.int32)
-            self.eng.upload_subset(self.N, ids, box, r[ids], orient[ids])
+        if hasattr(self.eng, "upload_select"):
+            self.eng.upload_select(box, r, orient)
+            self.h2d_bytes = int(r.nbytes + 108 * self.eng.slab_range()[3])  # every position + the selected particles' state
         else:  # stand-in engines of the CPU tests
             self.eng.upload(box, r, orient)
-        self.h2d_bytes = int(r[ids].nbytes + orient[ids].nbytes + ids.nbytes) if hasattr(self.eng, "slab_select") else 0
+            self.h2d_bytes = 0
         self._halo_cache = [None, None]
         self._rebuilds = 0
         if self.peer_halo:

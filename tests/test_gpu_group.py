@@ -172,3 +172,37 @@ def test_c_host_with_gpus_key(pp, tmp_path):
         assert p.returncode == 0, p.stderr[-2000:]
         outs.append((open(d / "last.rrr").read(), open(d / "energy.dat").read(), open(d / "acceptance.dat").read()))
     assert outs[0] == outs[1]
+
+
+def test_upload_select_from_pinned_and_pageable_memory(pp):
+    """pp_upload_select: a slab engine handed the whole configuration keeps the particles of its layers -- selected and
+    gathered by a kernel reading pinned host memory, or on the host from pageable memory -- exactly the set pp_slab_select
+    names, whatever the order they arrive in."""
+    import torch
+    box, r, m = pp.random_fluid(50000, 0.5, seed=6)
+    m9 = m.reshape(-1, 9)
+    r_pin, m_pin = torch.from_numpy(r.copy()).pin_memory().numpy(), torch.from_numpy(m9.copy()).pin_memory().numpy()
+    for rank, world in ((0, 2), (1, 3), (4, 5)):
+        results = []
+        for how in ("subset", "pinned", "pageable", "pinned again"):
+            e = pp.Engine(**PARAMS) if how != "pinned again" else results[1][2]
+            if how != "pinned again":
+                e.slab_setup(rank, world)
+            if how == "subset":
+                mine = e.slab_select(rank, world, box, r)
+                ids = np.flatnonzero(mine).astype(np.int32)
+                e.upload_subset(len(r), ids, box, r[ids], m9[ids])
+            elif how == "pageable":
+                e.upload_select(box, r, m9)
+            else:
+                e.upload_select(box, r_pin, m_pin)
+            ids_own, r_own, m_own = e.slab_download()
+            order = np.argsort(ids_own)
+            results.append(((e.slab_range(), e.total_bonds()), (ids_own[order], r_own[order], m_own[order]), e))
+        for res in results[1:]:
+            assert res[0] == results[0][0]
+            for a, b in zip(res[1], results[0][1]):
+                assert np.array_equal(a, b)
+        assert np.array_equal(results[0][1][1], r[results[0][1][0]])
+        for res in results[:3]:
+            res[2].close()
