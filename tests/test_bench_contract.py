@@ -12,7 +12,7 @@ from conftest import ROOT
 def test_reference_arm_json_line():
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "PatchyParticles")):
         pytest.skip("oracle/_ref not built")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "64k", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout.strip().split("\n")[-1])
