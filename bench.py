@@ -484,15 +484,19 @@ def measure(pkg, args, w, K, W, n_e2e, cpu_budget_s, ctx, headline):
     r_pin = torch.from_numpy(np.ascontiguousarray(r_now)).pin_memory()
     m_pin = torch.from_numpy(np.ascontiguousarray(m_now.reshape(-1, 9))).pin_memory()
     r_host, m_host = r_pin.numpy(), m_pin.numpy()
+    def e2e_step():
+        arm.upload(box_now, r_host, m_host)   # H2D of the step's input configuration + cell build
+        if box_moves:
+            arm.total_bonds()                 # the initial energy a box move is weighed against (main.c:55-61)
+        arm.sweep(1)                          # one MC step
+
     for i in range(2):
-        arm.upload(box_now, r_host, m_host)
-        arm.sweep(1)
+        e2e_step()
         arm.observables()
     barrier()
     t0 = time.perf_counter()
     for i in range(n_e2e):
-        arm.upload(box_now, r_host, m_host)   # H2D of the step's input configuration + cell build
-        arm.sweep(1)                          # one MC step
+        e2e_step()
         arm.observables()                     # D2H of the step's result (energy, counters)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -503,8 +507,7 @@ def measure(pkg, args, w, K, W, n_e2e, cpu_budget_s, ctx, headline):
     barrier()
     t0 = time.perf_counter()
     for i in range(n_rt):
-        arm.upload(box_now, r_host, m_host)
-        arm.sweep(1)
+        e2e_step()
         arm.download()
     barrier()
     rt_s = time.perf_counter() - t0
