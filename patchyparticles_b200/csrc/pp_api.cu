@@ -107,7 +107,7 @@ int ensure_state(pp_handle *h, size_t n, size_t n_ids, size_t n_records) {
 		off += align(cap * 9 * sizeof(double));
 	}
 	L.off_posf = off;
-	off += align(cap * sizeof(uint2));
+	off += align(cap * sizeof(uint4));
 	for(int k = 0; k < 2; k++) {
 		L.off_mig[k] = off;
 		off += align(n_records * 13 * sizeof(double));
@@ -120,7 +120,7 @@ int ensure_state(pp_handle *h, size_t n, size_t n_ids, size_t n_records) {
 	h->arena_bytes = off;
 	for(int k = 0; k < 3; k++) h->pos[k] = reinterpret_cast<double4 *>(h->arena + L.off_pos[k]);
 	for(int k = 0; k < 2; k++) h->ori[k] = reinterpret_cast<double *>(h->arena + L.off_ori[k]);
-	h->cb.posf = reinterpret_cast<uint2 *>(h->arena + L.off_posf);
+	h->cb.posf = reinterpret_cast<uint4 *>(h->arena + L.off_posf);
 	for(int k = 0; k < 2; k++) {
 		CUDA_OK(h, cudaMalloc(&h->pid[k], cap * sizeof(int)));
 		if(n_records) {

@@ -79,8 +79,8 @@ __global__ void k_zero_bonds(Counters *counters) {
 // is met once: the particle's own cell (slot_q > slot_p) and the 13 neighbour cells with (dx, dy, dz) > (0, 0, 0)
 // in lexicographic order, i.e. five columns -- (0, 0): the rest of the cell and the cell above it in z;
 // (0, +1), (+1, -1), (+1, 0), (+1, +1): three cells each.  Every candidate is first screened in FP32 from the
-// 8-byte fixed-point shadows (the same conservative screen as the sweep: squared distance below r_cut^2 + 2e-3,
-// shadow arithmetic good to 2e-4), so the FP64 position of a particle is fetched only for pairs that may be in
+// fixed-point shadows (box fractions; the same conservative screen as the sweep: squared distance below r_cut^2 + 2e-3,
+// shadow arithmetic good to 1e-5), so the FP64 position of a particle is fetched only for pairs that may be in
 // range and an orientation matrix only for a pair inside the bonding shell (p's side first; q's matrix only if
 // one of p's patches points at q, as the reference enters its inner loop, MC.c:249-255).  The global overlap
 // flag is polled by every thread: after the first overlap the rest returns at once, like the reference's
@@ -90,9 +90,6 @@ __global__ void k_zero_bonds(Counters *counters) {
 // with the left halo (dx = -1 is not in the half shell): every cross-boundary pair is counted once, on its left.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBondCellThreads = 256;
-
-__device__ __forceinline__ float shadow16_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); } // 2^23 + low half
-__device__ __forceinline__ float shadow16_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); } // 2^23 + high half
 
 // FP64 pair test of (sp, sq) in the reference's operation order (MC.c:233-262) -> bond count, overlap
 static __device__ __noinline__ void bond_pair_exact(const SimConst &sc, const double4 *__restrict__ pos, const double *__restrict__ ori, int sp, int sq,
@@ -111,7 +108,7 @@ static __device__ __noinline__ void bond_pair_exact(const SimConst &sc, const do
 }
 
 __global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
-		const int *__restrict__ cell_sorted, const double4 *__restrict__ pos, const double *__restrict__ ori, const uint2 *__restrict__ posf,
+		const int *__restrict__ cell_sorted, const double4 *__restrict__ pos, const double *__restrict__ ori, const uint4 *__restrict__ posf,
 		Counters *counters) {
 	// pairs that pass the FP32 screen are queued per warp and tested in FP64 by all its lanes together: the exact test is
 	// a few hundred instructions, and taken where it is found it would run with one or two lanes of the warp active
@@ -150,20 +147,15 @@ __global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __
 			se[1] = cs[iz + 1];
 			sb[2] = cs[zp];
 			se[2] = cs[zp + 1];
-			const uint2 sh = posf[sp];
-			const float ux = (float) (sc.cell_w[0] / 65535.), uy = (float) (sc.cell_w[1] / 65535.), uz = (float) (sc.cell_w[2] / 65535.);
-			const float wz = (float) sc.cell_w[2];
-			// neighbour minus own position: the 2^23 offsets of the shadow floats cancel in the differences
-			const float px = fmaf(-shadow16_lo(sh.x), ux, (float) dx * (float) sc.cell_w[0]);
-			const float py = fmaf(-shadow16_hi(sh.x), uy, (float) dy * (float) sc.cell_w[1]);
-			const float pz = -shadow16_lo(sh.y) * uz;
+			// neighbour minus own shadow, read as signed integers: the minimum-image separation in units of box / 2^32
+			const uint4 sh = posf[sp];
+			const float ux = (float) (sc.box[0] / 4294967296.), uy = (float) (sc.box[1] / 4294967296.), uz = (float) (sc.box[2] / 4294967296.);
 			const float thr = (float) sc.sqr_rcut + 2e-3f;
 #pragma unroll
 			for(int g = 0; g < 3; g++) {
-				const float oz = pz + (float) (g - 1) * wz;
 				for(int sq = sb[g]; sq < se[g]; sq++) {
-					const uint2 qh = posf[sq];
-					const float ax = fmaf(shadow16_lo(qh.x), ux, px), ay = fmaf(shadow16_hi(qh.x), uy, py), az = fmaf(shadow16_lo(qh.y), uz, oz);
+					const uint4 qh = posf[sq];
+					const float ax = shadow_sep(qh.x, sh.x, ux), ay = shadow_sep(qh.y, sh.y, uy), az = shadow_sep(qh.z, sh.z, uz);
 					if(fmaf(az, az, fmaf(ay, ay, ax * ax)) < thr) {
 						const int slot = atomicAdd(&s_queued[warp], 1);
 						if(slot < kQueue) s_queue[warp][slot] = make_int2(sp, sq);
@@ -194,7 +186,7 @@ __global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __
 	}
 }
 
-int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint2 *posf,
+int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint4 *posf,
 		Counters *counters, cudaStream_t st) {
 	k_zero_bonds<<<1, 1, 0, st>>>(counters);
 	const bool wide = (sc.slab || sc.nxl >= 4) && sc.n_side[1] >= 4 && sc.n_side[2] >= 4;
@@ -386,20 +378,19 @@ int launch_proposals(const SimConst &sc, int n, const ProposalIO &io, const int 
 }
 
 __global__ void k_commit(const __grid_constant__ SimConst sc, int slot, const double *__restrict__ disp, const double *__restrict__ orient, double4 *pos,
-		double *ori, uint2 *posf) {
+		double *ori, uint4 *posf) {
 	if(threadIdx.x == 0) {
 		double4 p = pos[slot];
 		p.x = __dadd_rn(p.x, disp[0]);
 		p.y = __dadd_rn(p.y, disp[1]);
 		p.z = __dadd_rn(p.z, disp[2]);
 		pos[slot] = p;
-		// the shadow follows (rank in the cell unchanged); if the particle left its cell the caller rebuilds the cells anyway
-		posf[slot] = cell_shadow(sc, p.x, p.y, p.z, (int) (posf[slot].y >> 16));
+		store_shadow_xyz(posf + slot, box_shadow(sc, p.x, p.y, p.z, slot)); // the shadow follows
 	}
 	if(threadIdx.x < 9) ori[9ll * slot + threadIdx.x] = orient[threadIdx.x];
 }
 
-int launch_commit(const SimConst &sc, int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, uint2 *posf, cudaStream_t st) {
+int launch_commit(const SimConst &sc, int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, uint4 *posf, cudaStream_t st) {
 	k_commit<<<1, 32, 0, st>>>(sc, slot, disp3, orient9, pos, ori, posf);
 	return 1;
 }

@@ -133,18 +133,19 @@ __device__ __forceinline__ int neighbourhood_total(const SimConst &sc, const int
 // bin of a non-empty cell in the work lists: colour-major, occupancy descending inside a colour.  A cell whose
 // neighbourhood does not fit the staging area of the thread-per-cell kernel is filed with the most crowded ones,
 // which always go to the tile kernel.
-__device__ __forceinline__ int work_bin(const SimConst &sc, int ix, int iy, int iz, int n, bool dense) {
+__device__ __forceinline__ int work_bin(const SimConst &sc, int ix, int iy, int iz, int n, bool dense, int nb_total) {
 	const int colour = ((ix + sc.x_lo) & 1) | ((iy & 1) << 1) | ((iz & 1) << 2); // parity of the GLOBAL layer
 	const int bucket = (dense || n >= kWorkBuckets) ? kWorkBuckets : n;            // 1 .. kWorkBuckets
-	return colour * kWorkBuckets + (kWorkBuckets - bucket);                         // big cells first
+	const int cls = nb_total > 0 ? min((nb_total - 1) >> 2, kWorkSub - 1) : 0;      // staged entries rounded up to four, in fours
+	return (colour * kWorkBuckets + (kWorkBuckets - bucket)) * kWorkSub + (kWorkSub - 1 - cls); // big cells first, big neighbourhoods first
 }
 
 // per cell: order its particles by id (insertion sort; a handful of particles), choose and count its work bin.
 // The bins are few and hot: they are counted per block in shared memory, one global atomic per bin and block.
 __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start, int *__restrict__ perm,
 		const int *__restrict__ pid_src, int *__restrict__ bin_count, int *__restrict__ cell_bin, int cells_max_occupancy, int cells_nb_cap) {
-	__shared__ int s_bin[8 * kWorkBuckets];
-	if(threadIdx.x < 8 * kWorkBuckets) s_bin[threadIdx.x] = 0;
+	__shared__ int s_bin[kWorkBins];
+	for(int b = threadIdx.x; b < kWorkBins; b += blockDim.x) s_bin[b] = 0;
 	__syncthreads();
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if(c < sc.n_cells) {
@@ -163,49 +164,50 @@ __global__ void __launch_bounds__(256) k_cell_order(const __grid_constant__ SimC
 				perm[k + 1] = src;
 			}
 			if(ix >= sc.own_lo && ix < sc.own_hi) { // halo cells are never moved here
-				const bool dense = (e - b <= cells_max_occupancy) && neighbourhood_total(sc, cell_start, ix, iy, iz) > cells_nb_cap;
-				const int bin = work_bin(sc, ix, iy, iz, e - b, dense);
+				const int nb_total = (e - b <= cells_max_occupancy) ? neighbourhood_total(sc, cell_start, ix, iy, iz) : 0;
+				const bool dense = nb_total > cells_nb_cap;
+				const int bin = work_bin(sc, ix, iy, iz, e - b, dense, dense ? 0 : nb_total);
 				cell_bin[c] = bin;
 				atomicAdd(&s_bin[bin], 1);
 			}
 		}
 	}
 	__syncthreads();
-	if(threadIdx.x < 8 * kWorkBuckets && s_bin[threadIdx.x]) atomicAdd(bin_count + threadIdx.x, s_bin[threadIdx.x]);
+	for(int b = threadIdx.x; b < kWorkBins; b += blockDim.x)
+		if(s_bin[b]) atomicAdd(bin_count + b, s_bin[b]);
 }
 
-// one warp: exclusive scan of the 8 * kWorkBuckets bins; work_start[colour] marks the colour boundaries
-__global__ void k_bins_scan(const int *__restrict__ bin_count, int *__restrict__ bin_start, int *__restrict__ ranges, int cells_max_occupancy,
-		int cells_mid_occupancy) {
-	__shared__ int s[8 * kWorkBuckets + 1];
-	if(threadIdx.x == 0) {
-		int run = 0;
-		for(int b = 0; b < 8 * kWorkBuckets; b++) {
-			s[b] = run;
-			run += bin_count[b];
-		}
-		s[8 * kWorkBuckets] = run;
+// one block of kWorkBins threads: exclusive scan of the bins
+__global__ void __launch_bounds__(kWorkBins) k_bins_scan(const int *__restrict__ bin_count, int *__restrict__ bin_start, int *__restrict__ ranges,
+		int cells_max_occupancy, int cells_mid_occupancy) {
+	__shared__ int s[kWorkBins + 1];
+	__shared__ int warp_sums[32];
+	{
+		int total;
+		const int ex = block_exclusive_scan(bin_count[threadIdx.x], warp_sums, total);
+		s[threadIdx.x] = ex;
+		if(threadIdx.x == 0) s[kWorkBins] = total;
 	}
 	__syncthreads();
-	for(int b = threadIdx.x; b <= 8 * kWorkBuckets; b += blockDim.x) bin_start[b] = s[b];
+	for(int b = threadIdx.x; b <= kWorkBins; b += blockDim.x) bin_start[b] = s[b];
 	if(threadIdx.x < 8) { // split each colour's list (occupancy descending): crowded cells, middle range, cells with <= cells_max_occupancy members
 		const int c = threadIdx.x, m1 = cells_max_occupancy < kWorkBuckets ? cells_max_occupancy : kWorkBuckets;
 		const int m2 = cells_mid_occupancy < m1 ? m1 : (cells_mid_occupancy < kWorkBuckets ? cells_mid_occupancy : kWorkBuckets);
-		const int split2 = s[c * kWorkBuckets + (kWorkBuckets - m2)], split1 = s[c * kWorkBuckets + (kWorkBuckets - m1)];
-		ranges[6 * c + 0] = s[c * kWorkBuckets];
+		const int split2 = s[(c * kWorkBuckets + (kWorkBuckets - m2)) * kWorkSub], split1 = s[(c * kWorkBuckets + (kWorkBuckets - m1)) * kWorkSub];
+		ranges[6 * c + 0] = s[c * kWorkBuckets * kWorkSub];
 		ranges[6 * c + 1] = split2;
 		ranges[6 * c + 2] = split2;
 		ranges[6 * c + 3] = split1;
 		ranges[6 * c + 4] = split1;
-		ranges[6 * c + 5] = s[(c + 1) * kWorkBuckets];
+		ranges[6 * c + 5] = s[(c + 1) * kWorkBuckets * kWorkSub];
 	}
 }
 
 // work lists: rank inside the block's share of a bin from shared memory, one global atomic per bin and block
 __global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
 		const int *__restrict__ bin_start, int *__restrict__ bin_fill, const int *__restrict__ cell_bin, int *__restrict__ work) {
-	__shared__ int s_cnt[8 * kWorkBuckets], s_base[8 * kWorkBuckets];
-	if(threadIdx.x < 8 * kWorkBuckets) s_cnt[threadIdx.x] = 0;
+	__shared__ int s_cnt[kWorkBins], s_base[kWorkBins];
+	for(int b = threadIdx.x; b < kWorkBins; b += blockDim.x) s_cnt[b] = 0;
 	__syncthreads();
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	int bin = -1, rank = 0;
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ Si
 		}
 	}
 	__syncthreads();
-	if(threadIdx.x < 8 * kWorkBuckets && s_cnt[threadIdx.x])
-		s_base[threadIdx.x] = bin_start[threadIdx.x] + atomicAdd(bin_fill + threadIdx.x, s_cnt[threadIdx.x]);
+	for(int b = threadIdx.x; b < kWorkBins; b += blockDim.x)
+		if(s_cnt[b]) s_base[b] = bin_start[b] + atomicAdd(bin_fill + b, s_cnt[b]);
 	__syncthreads();
 	if(bin >= 0) work[s_base[bin] + rank] = c;
 }
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(256) k_work_scatter(const __grid_constant__ Si
 __global__ void __launch_bounds__(256) k_cell_gather_pos(const __grid_constant__ SimConst sc, const int *__restrict__ perm,
 		const int *__restrict__ cell_of, const double4 *__restrict__ pos_src, const int *__restrict__ pid_src, double4 *__restrict__ pos_dst,
 		int *__restrict__ pid_dst, int *__restrict__ slot_of, int *__restrict__ cell_sorted, const int *__restrict__ cell_start,
-		uint2 *__restrict__ posf) {
+		uint4 *__restrict__ posf) {
 	const int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if(s >= sc.N) return;
 	const int src = perm[s];
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(256) k_cell_gather_pos(const __grid_constant__
 	slot_of[id] = s;
 	const int c = cell_of[src];
 	cell_sorted[s] = c;
-	posf[s] = cell_shadow(sc, p.x, p.y, p.z, s - cell_start[c]); // shadow used by the sweep's pre-screens
+	posf[s] = box_shadow(sc, p.x, p.y, p.z, s); // shadow used by the pre-screens of the sweep and of the bond count
 }
 
 __global__ void __launch_bounds__(256) k_cell_gather_ori(long long n9, const int *__restrict__ perm, const double *__restrict__ ori_src,
@@ -269,7 +271,7 @@ int launch_cell_build(const SimConst &sc, const CellBuffers &cb, const StateView
 	k_scan_add<<<n_tiles, kScanThreads, 0, st>>>(cb.cell_start, cb.tile_sums, nc);
 	k_cell_scatter<<<nb, 256, 0, st>>>(N, cb.cell_of, cb.cell_start, cb.cell_fill, cb.perm);
 	k_cell_order<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.perm, src.pid, cb.bins + kBinCount, cb.cell_fill, cells_max_occupancy, kCellsNbCap);
-	k_bins_scan<<<1, 160, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkRanges, cells_max_occupancy, cells_mid_occupancy);
+	k_bins_scan<<<1, kWorkBins, 0, st>>>(cb.bins + kBinCount, cb.bins + kBinStart, cb.bins + kWorkRanges, cells_max_occupancy, cells_mid_occupancy);
 	k_work_scatter<<<ncb, 256, 0, st>>>(sc, cb.cell_start, cb.bins + kBinStart, cb.bins + kBinFill, cb.cell_fill, cb.work);
 	k_cell_gather_pos<<<nb, 256, 0, st>>>(sc, cb.perm, cb.cell_of, src.pos, src.pid, dst.pos, dst.pid, slot_of, cb.cell_sorted, cb.cell_start, cb.posf);
 	const long long n9 = 9ll * N;

@@ -71,10 +71,10 @@ struct Vec3 {
 struct HaloMirror {
 	double4 *pos_l;       // left neighbour's position array; nullptr: no mirror (single engine)
 	double *ori_l;
-	uint2 *posf_l;
+	uint4 *posf_l;
 	double4 *pos_r;       // right neighbour's arrays (its left halo starts at slot 0)
 	double *ori_r;
-	uint2 *posf_r;
+	uint4 *posf_r;
 	const int *off_l_ptr; // where the left neighbour published the first slot of its right halo; nullptr: off_l holds it
 	int off_l;
 	int ls1, ls2, ls3;    // this engine's first owned layer is [ls1, ls2), its last owned layer starts at ls3
@@ -129,23 +129,28 @@ __device__ __forceinline__ int global_cell(const SimConst &sc, int ix, int iy, i
 	return (gx * sc.n_side[1] + iy) * sc.n_side[2] + iz;
 }
 
-// Fixed-point shadow of a position: offset inside its cell along x, y, z in units of cell_w / 65535
-// (16 bits each) and the particle's rank inside its cell.  Only the conservative FP32 pre-screens of
-// the thread-per-cell sweep kernel read it (quantisation + FP32 error of a squared separation
-// < 2e-4, screen bands 2e-3); every decision is taken in FP64.
-__device__ __forceinline__ unsigned shadow_coord(double r, double shift, double inv_box, int n_side) {
-	const double t = __dmul_rn(__dsub_rn(r, shift), inv_box);
-	const double g = __dmul_rn(__dsub_rn(t, floor(t)), (double) n_side);
-	int c = (int) g;
-	c = c < n_side ? c : n_side - 1;
-	return __double2uint_rn((g - (double) c) * 65535.0); // 0 .. 65535
+// Fixed-point shadow of a position: every coordinate as a 32-bit fraction of the box side, frac(r / box) * 2^32, and
+// the particle's slot in .w.  The number wraps with the periodic image, so the difference of two shadows read as a
+// signed integer IS the minimum-image separation in units of box / 2^32 -- no cell offsets, no image search, and the
+// same for every cell grid.  Only the conservative FP32 pre-screens of the sweep kernel and of the bond count read it
+// (truncation + FP32 error of a squared separation < 1e-5 for boxes up to a few thousand diameters, screen bands
+// 2e-3, tests/test_shadow_bounds.py); every decision is taken in FP64.
+__device__ __forceinline__ unsigned box_fraction(double r, double inv_box) {
+	const double t = __dmul_rn(r, inv_box);
+	const double f = __dsub_rn(t, floor(t));                  // [0, 1]
+	return __double2uint_rz(__dmul_rn(f, 4294967296.0));      // saturates at 2^32 - 1
 }
-__device__ __forceinline__ uint2 cell_shadow(const SimConst &sc, double x, double y, double z, int rank) {
-	const unsigned qx = shadow_coord(x, sc.shift[0], sc.inv_box[0], sc.n_side[0]);
-	const unsigned qy = shadow_coord(y, sc.shift[1], sc.inv_box[1], sc.n_side[1]);
-	const unsigned qz = shadow_coord(z, sc.shift[2], sc.inv_box[2], sc.n_side[2]);
-	return make_uint2(qx | (qy << 16), qz | ((unsigned) rank << 16));
+__device__ __forceinline__ uint4 box_shadow(const SimConst &sc, double x, double y, double z, int slot) {
+	return make_uint4(box_fraction(x, sc.inv_box[0]), box_fraction(y, sc.inv_box[1]), box_fraction(z, sc.inv_box[2]), (unsigned) slot);
 }
+// the coordinates of a shadow change, the slot in .w stays (a 8-byte and a 4-byte store: .w is never touched, so a
+// copy of the layer held by another engine keeps its own slot numbers)
+__device__ __forceinline__ void store_shadow_xyz(uint4 *dst, const uint4 v) {
+	*reinterpret_cast<uint2 *>(dst) = make_uint2(v.x, v.y);
+	reinterpret_cast<unsigned *>(dst)[2] = v.z;
+}
+// shadow separation -> FP32 separation: (float) (int) (q - p) * (box / 2^32)
+__device__ __forceinline__ float shadow_sep(unsigned q, unsigned p, float unit) { return (float) (int) (q - p) * unit; }
 
 // rint(d / box) as the reference computes it (MC.c:234-236), without the division in the common
 // case: rint(d * inv_box) can only differ from rint(d / box) when the quotient is within a couple
@@ -374,11 +379,11 @@ __device__ __forceinline__ double4 ld_pos(const double4 *__restrict__ pos, int s
 }
 
 // the halo copy of an accepted move (see HaloMirror); off_l: first slot of the left neighbour's right halo
-__device__ __forceinline__ void mirror_state(const HaloMirror &hm, int off_l, int sp, const Vec3 &p, const uint2 shadow, const double *m) {
+__device__ __forceinline__ void mirror_state(const HaloMirror &hm, int off_l, int sp, const Vec3 &p, const uint4 shadow, const double *m) {
 	if(hm.pos_l == nullptr) return;
 	double4 *tp;
 	double *to;
-	uint2 *tf;
+	uint4 *tf;
 	int d;
 	if(sp < hm.ls2) {
 		tp = hm.pos_l;
@@ -397,7 +402,7 @@ __device__ __forceinline__ void mirror_state(const HaloMirror &hm, int off_l, in
 	q[0] = p.x;
 	q[1] = p.y;
 	q[2] = p.z;
-	tf[d] = shadow;
+	store_shadow_xyz(tf + d, shadow);
 #pragma unroll
 	for(int k = 0; k < 9; k++) to[9ll * d + k] = m[k];
 }

@@ -12,13 +12,17 @@ struct StateView {
 	int *pid;     // particle id per slot
 };
 
-// work lists of the sweep: 8 colours x kWorkBuckets occupancy buckets (descending occupancy)
+// work lists of the sweep: 8 colours x kWorkBuckets occupancy buckets (descending occupancy) x kWorkSub classes of the
+// neighbourhood size (descending, four neighbours wide: the lanes of a warp of the thread-per-cell kernel then run the
+// same number of trials over the same number of staged entries)
 constexpr int kWorkBuckets = 16;
-constexpr int kCellsNbCap = 48; // neighbours the thread-per-cell sweep kernel can stage; cells with more go to the tile kernel
-constexpr int kBinCount = 0;                              // [8 * kWorkBuckets] cells per bin
-constexpr int kBinStart = 8 * kWorkBuckets;               // [8 * kWorkBuckets + 1] exclusive prefix
-constexpr int kBinFill = kBinStart + 8 * kWorkBuckets + 1; // [8 * kWorkBuckets] scatter cursors
-constexpr int kWorkRanges = kBinFill + 8 * kWorkBuckets;  // [8][6] per colour: {begin, end} of the crowded cells (8 lanes per cell or the tile kernel),
+constexpr int kWorkSub = 8;
+constexpr int kWorkBins = 8 * kWorkBuckets * kWorkSub;
+constexpr int kCellsNbCap = 32; // neighbours the thread-per-cell sweep kernel can stage; cells with more go to the tile kernel
+constexpr int kBinCount = 0;                              // [kWorkBins] cells per bin
+constexpr int kBinStart = kWorkBins;                      // [kWorkBins + 1] exclusive prefix
+constexpr int kBinFill = kBinStart + kWorkBins + 1;       // [kWorkBins] scatter cursors
+constexpr int kWorkRanges = kBinFill + kWorkBins;         // [8][6] per colour: {begin, end} of the crowded cells (8 lanes per cell or the tile kernel),
                                                           // of the middle range (4 lanes per cell) and of the sparsely populated cells (one thread per cell)
 constexpr int kBinInts = kWorkRanges + 48;
 
@@ -32,7 +36,7 @@ struct CellBuffers {
 	int *perm;        // N
 	int *work;        // n_cells: non-empty cells grouped by colour, occupancy descending
 	int *bins;        // kBinInts
-	uint2 *posf;      // N: 16-bit fixed-point position inside its cell (x, y, z) + rank in the cell (pre-screens only)
+	uint4 *posf;      // N: fixed-point shadow of each slot: box fractions x, y, z (32 bits each) + the slot (pre-screens only)
 };
 
 // A pre-generated roto-translation proposal (MC.c:312-324): rotation matrix R (new = old . R),
@@ -75,7 +79,7 @@ int launch_sweep_fused(const SimConst &sc, const int *ranges, long long max_item
 
 // K3: full bond count + overlap flag into counters->bonds / counters->overlap (zeroed by the launcher)
 // (posf: the shadows of the same slots; nullptr or a grid with fewer than four cells on an axis: the tile kernel without the FP32 screen)
-int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint2 *posf,
+int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint4 *posf,
 		Counters *counters, cudaStream_t st);
 // per-particle bonded-neighbour counts (indexed by particle id)
 int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, int *neighbours,
@@ -87,7 +91,7 @@ int launch_rescale(int N, const double4 *src, double4 *dst, double fx, double fy
 // K5: proposal evaluator against the frozen configuration
 int launch_proposals(const SimConst &sc, int n, const ProposalIO &io, const int *cell_start, const double4 *pos, const double *ori, const int *slot_of,
 		cudaStream_t st);
-int launch_commit(const SimConst &sc, int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, uint2 *posf, cudaStream_t st);
+int launch_commit(const SimConst &sc, int slot, const double *disp3, const double *orient9, double4 *pos, double *ori, uint4 *posf, cudaStream_t st);
 
 // K6: Gram-Schmidt on every orientation matrix
 int launch_orthonormalise(int N, double *ori, cudaStream_t st);
@@ -105,6 +109,7 @@ int launch_records_push(const double *outbox, const int *counts, int which, int 
 		unsigned long long epoch, unsigned int *done, cudaStream_t st);
 int launch_records_pull(const double *mbox, const int *my_count, const unsigned long long *flag, unsigned long long epoch, int cap, double *inbox,
 		int *in_count, int *status, cudaStream_t st);
+int launch_shadow_slots(uint4 *posf, int begin, int end, cudaStream_t st);
 int launch_gather_ints(const int *src, const int *idx, int n, int *out, cudaStream_t st);
 
 // upload / download helpers (caller order <-> slot order)

@@ -180,6 +180,19 @@ __global__ void __launch_bounds__(256) k_records_pull(const double *__restrict__
 	if(blockIdx.x == 0 && threadIdx.x == 0) *in_count = n;
 }
 
+// send / recv transport: a halo layer arrives as a copy of the owner's slices, shadows included; their .w must name the
+// slots of THIS engine's arrays
+__global__ void __launch_bounds__(256) k_shadow_slots(uint4 *__restrict__ posf, int begin, int end) {
+	const int s = begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if(s < end) posf[s].w = (unsigned) s;
+}
+
+int launch_shadow_slots(uint4 *posf, int begin, int end, cudaStream_t st) {
+	if(end <= begin) return 0;
+	k_shadow_slots<<<(end - begin + 255) / 256, 256, 0, st>>>(posf, begin, end);
+	return 1;
+}
+
 struct GatherIdx {
 	int idx[8];
 };

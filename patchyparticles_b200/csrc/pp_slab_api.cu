@@ -134,7 +134,7 @@ int slab_build_mirror(pp_handle *h) {
 		const pp_peer_info &L = h->peer_layout[side];
 		double4 *pos = reinterpret_cast<double4 *>(a + L.off_pos[h->cp]);
 		double *ori = reinterpret_cast<double *>(a + L.off_ori[h->co]);
-		uint2 *posf = reinterpret_cast<uint2 *>(a + L.off_posf);
+		uint4 *posf = reinterpret_cast<uint4 *>(a + L.off_posf);
 		if(side == 0) {
 			hm.pos_l = pos;
 			hm.ori_l = ori;
@@ -215,6 +215,12 @@ int slab_block(pp_handle *h, int cx) {
 		prof_end(h, PP_K_RNG, nr);
 	}
 	if(h->peer_connected && slab_wait(h, cx == 0 ? kSideLeft : kSideRight)) return 1;
+	if(!h->peer_connected) { // send / recv transport: the driver has just copied the neighbour's layer into the halo this block reads
+		const int b = cx == 0 ? h->layer_slots[0] : h->layer_slots[4], e = cx == 0 ? h->layer_slots[1] : h->layer_slots[5];
+		const int nf = launch_shadow_slots(h->cb.posf, b, e, h->stream);
+		h->launches[PP_K_HALO] += nf;
+		h->total_launches += nf;
+	}
 	prof_begin(h);
 	const int nl = launch_passes(h, sc, 4 * cx, 4);
 	prof_end(h, PP_K_SWEEP, nl);

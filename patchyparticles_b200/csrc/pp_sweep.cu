@@ -129,7 +129,7 @@ __host__ __device__ constexpr int sweep_threads() {
 template<int G>
 __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) k_sweep_pass(const __grid_constant__ SimConst sc, const int *__restrict__ range,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals,
-		double4 *pos, double *ori, uint2 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
+		double4 *pos, double *ori, uint4 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
 	constexpr int kThreads = sweep_threads<G>();
 	constexpr int kTiles = kThreads / G;
 	__shared__ TileSmem<G> s_tile[kTiles];
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(sweep_threads<G>(), 512 / sweep_threads<G>()) 
 					p[0] = p_new.x;
 					p[1] = p_new.y;
 					p[2] = p_new.z;
-					const uint2 moved = cell_shadow(sc, p_new.x, p_new.y, p_new.z, pick);
-					posf[sp] = moved;
+					const uint4 moved = box_shadow(sc, p_new.x, p_new.y, p_new.z, sp);
+					store_shadow_xyz(posf + sp, moved);
 					mirror_state(hm, hm_off, sp, p_new, moved, ts.m_new);
 					if(staged) {
 						ts.x[j_self] = p_new.x;

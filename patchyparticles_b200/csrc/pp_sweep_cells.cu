@@ -4,24 +4,25 @@
 // pp_sweep.cu (both are checked against the serial restatement in oracle/pp_oracle.c); what changes
 // is the mapping onto the machine and the arithmetic of the screens.
 //   G = 1  a thread walks its cell's trials on its own, so nothing is computed redundantly, shuffled or
-//          reduced: about half the warp instructions per trial of the tile kernel.  The price is a serial
-//          chain per cell, so the cell build routes the sparsely populated cells here (at most M members,
-//          at most kCellsNbCap staged neighbours: >95 % of the cells of a fluid) ...
+//          reduced.  The price is a serial chain per cell, so the cell build routes the sparsely populated
+//          cells here (at most M members, a neighbourhood that fits the staging area: >95 % of the cells of
+//          a fluid) ...
 //   G = 8  ... and the crowded ones to the 8-lane configuration, whose lanes split the nine columns of the
 //          neighbourhood and which also stages the cell's proposals and the FP64 state of its own particles
-//          (shortest chain per trial).  The two launches of a colour pass run concurrently on two streams.
+//          (shortest chain per trial).  One launch per colour pass runs the configurations side by side.
 // The work list hands consecutive groups cells of equal occupancy, which keeps the lanes of a warp in the same
-// trial.  No TMA: the staging is a gather of 8-byte items from ~27 short runs per cell, not a tile; cp.async
+// trial.  No TMA: the staging is a gather of 16-byte items from nine short runs per cell, not a tile; cp.async
 // (LDGSTS) is the fire-and-forget primitive that fits it.
 //
-//   per cell   the shadow positions (8 bytes: 16-bit fixed-point offset inside the cell + rank in the
-//              cell) of the 27-cell neighbourhood are brought into shared memory with cp.async -- all
-//              copies in flight at once, one wait; each entry is tagged with its neighbour-cell code;
-//   per trial  1. FP32 distance screen of the staged neighbours for the old and the new position: a
-//                 new position closer than 1 - 2e-3 (squared) to a neighbour is rejected on the spot,
-//                 a pair is a candidate when its squared distance is below r_cut^2 + 2e-3 (the
-//                 shadow arithmetic is good to 2e-4, so no pair the FP64 test would put inside the
-//                 shell, or flag as overlapping, is ever dropped);
+//   per cell   the shadows (pp_common.cuh: box fractions of x, y, z as 32-bit integers + the slot) of the 27-cell
+//              neighbourhood are brought into shared memory with cp.async.  A column of three cells along z is one
+//              contiguous run of slots (two at the box edge), so staging is nine run copies -- all in flight at once,
+//              one wait -- and the staged entry needs no tag: shadow differences are minimum-image separations;
+//   per trial  1. FP32 distance screen of the staged neighbours for the old and the new position, four
+//                 entries per iteration (the list is padded with far-away entries): a new position closer than
+//                 1 - 2e-3 (squared) to a neighbour is rejected on the spot, a pair is a candidate when its
+//                 squared distance is below r_cut^2 + 2e-3 (the shadow arithmetic is good to 1e-5, so no pair the
+//                 FP64 test would put inside the shell, or flag as overlapping, is ever dropped);
 //              2. FP32 orientation screen of the candidates (own matrix only): most pairs in the
 //                 shell cannot bond because no patch of the moved particle points at them;
 //              3. FP64, reference operation order, on what is left: overlap of the new position
@@ -34,15 +35,8 @@
 namespace pp {
 
 constexpr int kCellThreads = 64;
-constexpr int kNbCap = kCellsNbCap;          // staged neighbours per cell; the cell build routes denser cells to the tile kernel
-constexpr int kCandCap = kCellsNbCap;        // candidates per trial (at most one entry per neighbour)
-constexpr float kScreenBand = 2e-3f;         // safety band of the FP32 screens (error of the shadow arithmetic < 2e-4)
+constexpr float kScreenBand = 2e-3f;         // safety band of the FP32 screens (error of the shadow arithmetic < 1e-5)
 constexpr unsigned kNearOld = 0x40u, kNearNew = 0x80u, kIdxMask = 0x3fu;
-static_assert(kNbCap <= 64, "candidate entries index the staging area with 6 bits");
-
-// A 16-bit shadow coordinate q as the float 2^23 + q (one PRMT); the caller folds the 2^23 into its FMA.
-__device__ __forceinline__ float shadow_lo(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); }
-__device__ __forceinline__ float shadow_hi(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); }
 
 // May one of the four patches of the particle with (FP32) matrix mf point at a neighbour at separation
 // (x, y, z), |.|^2 = d2 ?  d . (M b_i) = (M^T d) . b_i with b_i = (+-1, +-1, +-1) * base_z (system.c:23-31);
@@ -63,17 +57,10 @@ struct CellBlockCounters {
 	unsigned long long w_tries, w_accepted, pair_checks;
 };
 
-// shadow of a staged neighbour -> FP32 position relative to the home cell's origin
-__device__ __forceinline__ void shadow_position(const uint2 q, const float4 off, float ux, float uy, float uz, float &x, float &y, float &z) {
-	x = fmaf(shadow_lo(q.x), ux, off.x);
-	y = fmaf(shadow_hi(q.x), uy, off.y);
-	z = fmaf(shadow_lo(q.y), uz, off.z);
-}
-
-constexpr int kFarCode = 27; // tag of an entry that must not pair with anything: its cell offset is far outside the screens
-
-// staging capacity of one lane (neighbours per lane); a cell whose neighbourhood does not fit takes the serial path
-__host__ __device__ constexpr int lane_cap(int G) { return G == 1 ? kCellsNbCap : (G == 2 ? 32 : 24); }
+// staging capacity of one lane (neighbours per lane, a multiple of 4); the cell build routes a sparsely populated cell
+// whose neighbourhood exceeds lane_cap(1) to the 8-lane configuration, a cell that does not fit there takes the serial path
+__host__ __device__ constexpr int lane_cap(int G) { return G == 1 ? kCellsNbCap : (G == 2 ? 24 : (G == 4 ? 20 : 16)); }
+static_assert(kCellsNbCap % 4 == 0 && kCellsNbCap <= 64, "candidate entries index the staging area with 6 bits; the screen loop takes four entries at a time");
 
 // Latency configuration (G >= 4): the proposals of the cell's trials and the FP64 state of its own particles are
 // staged too, so that a trial of a crowded cell does not wait for global memory between its steps.
@@ -88,10 +75,8 @@ struct OwnStage {
 // shared memory of one block (64 threads) running G lanes per cell
 template<int G>
 struct CellSmem {
-	uint2 stage[lane_cap(G)][kCellThreads];        // [entry][thread]: shadow of a staged neighbour
-	unsigned char tag[lane_cap(G)][kCellThreads];  // its neighbour-cell code, 0 .. 26
+	uint4 stage[lane_cap(G)][kCellThreads];        // [entry][thread]: shadow of a staged neighbour
 	unsigned char cand[lane_cap(G)][kCellThreads];
-	float4 off[28];                                // offset of neighbour cell `code` from the home cell, minus 2^23 shadow units
 	CellBlockCounters cnt;
 	OwnStage<max_own(G)> own[G >= 4 ? kCellThreads / G : 1];
 };
@@ -103,17 +88,16 @@ struct CellSmem {
 // fill the machine.
 template<int G>
 __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst &sc, const int w_begin, const int w_end, const int block, const int n_blocks,
-		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori, uint2 *posf,
+		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori, uint4 *posf,
 		Counters *__restrict__ counters, const HaloMirror &hm) {
 	constexpr int kCap = lane_cap(G);
 	constexpr bool kOwn = G >= 4;
 	constexpr int kMaxOwn = max_own(G);
 	constexpr int kGroups = kCellThreads / G;
+	constexpr int kCols = (9 + G - 1) / G;  // columns of the neighbourhood per lane
 	constexpr int kOwner = 4 % G; // the lane that stages the home column (c = 4) holds the moved particle's entry and does the book-keeping
-	uint2 (&s_stage)[kCap][kCellThreads] = sm.stage;
-	unsigned char (&s_tag)[kCap][kCellThreads] = sm.tag;
+	uint4 (&s_stage)[kCap][kCellThreads] = sm.stage;
 	unsigned char (&s_cand)[kCap][kCellThreads] = sm.cand;
-	float4 (&s_off)[28] = sm.off;
 	CellBlockCounters &s_cnt = sm.cnt;
 	OwnStage<kMaxOwn> *s_own = sm.own;
 	const int tid = threadIdx.x;
@@ -125,16 +109,13 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 	const int owner_lane = ((tid & 31) & ~(G - 1)) + kOwner; // warp lane of the group's owner
 	const bool is_owner = gl == kOwner;
 	if(tid == 0) s_cnt = CellBlockCounters{0, 0, 0, 0, 0, 0, 0, 0};
-	const float ux = (float) (sc.cell_w[0] / 65535.), uy = (float) (sc.cell_w[1] / 65535.), uz = (float) (sc.cell_w[2] / 65535.); // shadow units
-	if(tid < 28) {
-		const double far = tid == kFarCode ? 1e4 : 0.;
-		s_off[tid] = make_float4((float) ((double) (tid / 9 - 1) * sc.cell_w[0] - 8388608. * (double) ux + far),
-				(float) ((double) ((tid / 3) % 3 - 1) * sc.cell_w[1] - 8388608. * (double) uy),
-				(float) ((double) (tid % 3 - 1) * sc.cell_w[2] - 8388608. * (double) uz), 0.f);
-	}
 	__syncthreads();
 
 	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
+	const float ux = (float) (sc.box[0] / 4294967296.), uy = (float) (sc.box[1] / 4294967296.), uz = (float) (sc.box[2] / 4294967296.); // shadow units
+	// box fraction (x) of the cell origins: layer gx starts at shift / box + gx / nx
+	const float frac_w = 4294967296.f / (float) sc.n_side[0];
+	const unsigned shift_fx = box_fraction(sc.shift[0], sc.inv_box[0]);
 	const float thr = (float) sc.sqr_rcut + kScreenBand;
 	const float core_lo = 1.f - kScreenBand, core_hi = 1.f + kScreenBand; // certain overlap below, certain clearance above
 	// (M^T d . b_i)^2 > cosmax^2 d^2 / base_z^2 with a relative band; -1 disables the screen (every pair in range goes to FP64)
@@ -144,6 +125,24 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 	for(int wi = w_begin + block * kGroups + tid / G; wi < w_end; wi += n_blocks * kGroups) {
 		const int cell = work[wi];
 		const int ix = cell / nyz, iy = (cell - ix * nyz) / nz, iz = cell - ix * nyz - iy * nz;
+		// a column of the neighbourhood (three cells along z) is one run of slots, [a0, a1), plus at the two ends of the
+		// box the wrapped cell zw; the loads of all the lane's columns are issued together
+		const int z_lo = iz > 0 ? iz - 1 : 0, z_hi = iz < nz - 1 ? iz + 1 : nz - 1;
+		const bool edge = iz == 0 || iz == nz - 1;
+		const int zw = iz == 0 ? nz - 1 : 0;
+		int a0[kCols], a1[kCols];
+#pragma unroll
+		for(int k = 0; k < kCols; k++) {
+			const int c = gl + k * G;
+			a0[k] = a1[k] = 0;
+			if(c < 9) {
+				int cx = ix + c / 3 - 1;
+				if(!sc.slab) cx = wrap_cell(cx, sc.nxl); // (slab: an owned layer always has both x neighbours in the held range)
+				const int *cs = cell_start + (cx * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
+				a0[k] = cs[z_lo];
+				a1[k] = cs[z_hi + 1];
+			}
+		}
 		const int first = cell_start[cell];
 		const int n_here = cell_start[cell + 1] - first;
 		const bool own_staged = kOwn && n_here <= kMaxOwn;
@@ -163,22 +162,15 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 				prefetch_l2(ori + 9ll * (first + t) + 8);
 			}
 
-		// ---- stage this lane's columns of the neighbourhood (three cells each): all copies in flight, one wait ----
+		// ---- stage this lane's columns: run copies, all in flight, one wait ----------------------------------
 		int total = 0, self_base = 0;
-		const int z0 = wrap_cell(iz - 1, nz), z2 = wrap_cell(iz + 1, nz);
-#pragma unroll 1
-		for(int c = gl; c < 9; c += G) {
-			int cx = ix + c / 3 - 1;
-			if(!sc.slab) cx = wrap_cell(cx, sc.nxl); // (slab: an owned layer always has both x neighbours in the held range)
-			const int *cs = cell_start + (cx * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
-			const int b0 = cs[z0], n0 = cs[z0 + 1] - b0, b1 = cs[iz], n01 = n0 + cs[iz + 1] - b1, b2 = cs[z2], n_col = n01 + cs[z2 + 1] - b2;
-			if(c == 4) self_base = total + n0;
-			for(int k = 0; k < n_col; k++, total++)
+#pragma unroll
+		for(int k = 0; k < kCols; k++) {
+			const int c = gl + k * G;
+			if(c == 4) self_base = total + (first - a0[k]);
+			for(int s = a0[k]; s < a1[k]; s++, total++)
 				if(total < kCap) {
-					const int seg = (k >= n0) + (k >= n01);
-					const int s = k + (seg == 0 ? b0 : (seg == 1 ? b1 - n0 : b2 - n01));
-					__pipeline_memcpy_async(&s_stage[total][tid], posf + s, 8);
-					s_tag[total][tid] = (unsigned char) (c * 3 + seg);
+					__pipeline_memcpy_async(&s_stage[total][tid], posf + s, 16);
 					if(kOwn) { // FP64 state of a possible bonding partner: towards L2
 						prefetch_l2(pos + s);
 						prefetch_l2(ori + 9ll * s);
@@ -186,12 +178,31 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 					}
 				}
 		}
+		if(edge) { // first / last cell along z: the periodic neighbour sits at the other end of the column
+#pragma unroll 1
+			for(int c = gl; c < 9; c += G) {
+				int cx = ix + c / 3 - 1;
+				if(!sc.slab) cx = wrap_cell(cx, sc.nxl);
+				const int *cs = cell_start + (cx * ny + wrap_cell(iy + c % 3 - 1, ny)) * nz;
+				const int e = cs[zw + 1];
+				for(int s = cs[zw]; s < e; s++, total++)
+					if(total < kCap) __pipeline_memcpy_async(&s_stage[total][tid], posf + s, 16);
+			}
+		}
 		__pipeline_commit();
 		bool staged = total <= kCap;
 		if(G > 1) {
 #pragma unroll
 			for(int o = G / 2; o > 0; o >>= 1) staged &= (bool) __shfl_xor_sync(gmask, (int) staged, o);
 		}
+		// a far-away entry (half a box along x from the cell's centre): pads the list to a multiple of four and stands in
+		// for the moved particle itself
+		int gx = ix + sc.x_lo;
+		gx -= (gx >= sc.n_side[0]) ? sc.n_side[0] : 0;
+		const uint4 far = make_uint4(shift_fx + (unsigned) (((float) gx + 0.5f) * frac_w) + 0x80000000u, 0u, 0u, 0xffffffffu);
+		const int total4 = (total + 3) & ~3;
+		if(staged)
+			for(int j = total; j < total4; j++) s_stage[j][tid] = far;
 		__pipeline_wait_prior(0);
 		if(kOwn) __syncwarp(gmask); // every lane's copies have landed
 
@@ -218,34 +229,38 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 			const unsigned long long Wfix = (unsigned long long) pr->wfix;
 			if(is_owner) tl.wt += Wfix;
 			const int j_self = self_base + pick; // meaningful on the owner lane only
-			float fox, foy, foz;
-			shadow_position(s_stage[is_owner ? j_self : 0][tid], s_off[13], ux, uy, uz, fox, foy, foz);
+			uint4 self = s_stage[is_owner ? j_self : 0][tid];
 			if(G > 1) {
-				fox = __shfl_sync(gmask, fox, owner_lane);
-				foy = __shfl_sync(gmask, foy, owner_lane);
-				foz = __shfl_sync(gmask, foz, owner_lane);
+				self.x = __shfl_sync(gmask, self.x, owner_lane);
+				self.y = __shfl_sync(gmask, self.y, owner_lane);
+				self.z = __shfl_sync(gmask, self.z, owner_lane);
 			}
-			const float fnx = fox + (float) dx, fny = foy + (float) dy, fnz = foz + (float) dz;
+			const float fdx = (float) dx, fdy = (float) dy, fdz = (float) dz;
 
 			// ---- 1. FP32 distance screen over the staged neighbourhood ---------------------
-			if(is_owner) s_tag[j_self][tid] = (unsigned char) kFarCode; // the moved particle itself: out of everybody's range
+			if(is_owner) s_stage[j_self][tid] = far; // the moved particle itself: out of everybody's range
 			int n_cand = 0;
-			bool ovl = false;
-			for(int j = 0; j < total; j++) {
-				float qx, qy, qz;
-				shadow_position(s_stage[j][tid], s_off[s_tag[j][tid]], ux, uy, uz, qx, qy, qz);
-				const float ax = qx - fox, ay = qy - foy, az = qz - foz;
-				const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
-				const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
-				const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
-				ovl |= d2n < core_lo;
-				if(fminf(d2o, d2n) < thr) s_cand[n_cand++][tid] = (unsigned char) j; // n_cand <= total <= kCap
+			float d2n_min = 1e30f;
+			for(int j0 = 0; j0 < total4; j0 += 4) {
+#pragma unroll
+				for(int u = 0; u < 4; u++) {
+					const uint4 q = s_stage[j0 + u][tid];
+					const float ax = shadow_sep(q.x, self.x, ux), ay = shadow_sep(q.y, self.y, uy), az = shadow_sep(q.z, self.z, uz);
+					const float bx = ax - fdx, by = ay - fdy, bz = az - fdz;
+					const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
+					const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
+					d2n_min = fminf(d2n_min, d2n);
+					if(fminf(d2o, d2n) < thr) s_cand[n_cand++][tid] = (unsigned char) (j0 + u); // n_cand <= total <= kCap
+				}
 			}
-			if(is_owner) s_tag[j_self][tid] = 13;
 			tl.checks += 2ull * (unsigned long long) (total - (is_owner ? 1 : 0));
+			bool ovl = d2n_min < core_lo;
 			if(G > 1) ovl = __any_sync(gmask, ovl);
 			if(ovl) { // overlapping beyond any FP32 doubt: rejected whatever the bonds (MC.c:296-299, 332)
-				if(is_owner) tl.ovl++;
+				if(is_owner) {
+					s_stage[j_self][tid] = self;
+					tl.ovl++;
+				}
 				continue;
 			}
 
@@ -272,10 +287,9 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 				}
 				for(int c0 = 0; c0 < n_cand; c0++) {
 					const unsigned j = s_cand[c0][tid];
-					float qx, qy, qz;
-					shadow_position(s_stage[j][tid], s_off[s_tag[j][tid]], ux, uy, uz, qx, qy, qz);
-					const float ax = qx - fox, ay = qy - foy, az = qz - foz;
-					const float bx = qx - fnx, by = qy - fny, bz = qz - fnz;
+					const uint4 q = s_stage[j][tid];
+					const float ax = shadow_sep(q.x, self.x, ux), ay = shadow_sep(q.y, self.y, uy), az = shadow_sep(q.z, self.z, uz);
+					const float bx = ax - fdx, by = ay - fdy, bz = az - fdz;
 					const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
 					const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
 					unsigned keep = 0u;
@@ -290,11 +304,7 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 #pragma unroll 1
 			for(int c0 = 0; c0 < n_exact && !ovl; c0++) {
 				const unsigned e = s_cand[c0][tid];
-				const int code = s_tag[e & kIdxMask][tid], c9 = code / 3; // slot = first of its cell + rank
-				int ncx = ix + c9 / 3 - 1;
-				if(!sc.slab) ncx = wrap_cell(ncx, sc.nxl);
-				const int ncell = (ncx * ny + wrap_cell(iy + c9 % 3 - 1, ny)) * nz + wrap_cell(iz + code - 3 * c9 - 1, nz);
-				const int sq = cell_start[ncell] + (int) (s_stage[e & kIdxMask][tid].y >> 16);
+				const int sq = (int) s_stage[e & kIdxMask][tid].w; // the shadow carries its slot
 				const double4 q4 = pos[sq];
 				if(e & kNearNew) {
 					Vec3 d;
@@ -317,31 +327,37 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 				ovl = (packed >> 16) != 0u;
 			}
 			if(ovl) { // hard-core overlap: rejected whatever the bonds (MC.c:296-299, 332)
-				if(is_owner) tl.ovl++;
+				if(is_owner) {
+					s_stage[j_self][tid] = self;
+					tl.ovl++;
+				}
 				continue;
 			}
 
 			// ---- 4. Metropolis (MC.c:332-339) ------------------------------------------------
 			const int dE = b_old - b_new; // energy = -bonds
-			if(is_owner && (dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1])) {
-				double *p = reinterpret_cast<double *>(pos + sp); // x, y, z; the id in .w stays
-				p[0] = p_new.x;
-				p[1] = p_new.y;
-				p[2] = p_new.z;
-				const uint2 moved = cell_shadow(sc, p_new.x, p_new.y, p_new.z, pick);
-				posf[sp] = moved;
-				s_stage[j_self][tid] = moved;
+			if(is_owner) {
+				if(dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
+					double *p = reinterpret_cast<double *>(pos + sp); // x, y, z; the id in .w stays
+					p[0] = p_new.x;
+					p[1] = p_new.y;
+					p[2] = p_new.z;
+					const uint4 moved = box_shadow(sc, p_new.x, p_new.y, p_new.z, sp);
+					store_shadow_xyz(posf + sp, moved);
+					s_stage[j_self][tid] = moved;
 #pragma unroll
-				for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
-				mirror_state(hm, hm_off, sp, p_new, moved, mn);
-				if(own_staged) {
-					os.pos[pick] = make_double4(p_new.x, p_new.y, p_new.z, p4.w);
+					for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
+					mirror_state(hm, hm_off, sp, p_new, moved, mn);
+					if(own_staged) {
+						os.pos[pick] = make_double4(p_new.x, p_new.y, p_new.z, p4.w);
 #pragma unroll
-					for(int k = 0; k < 9; k++) os.ori[9 * pick + k] = mn[k];
+						for(int k = 0; k < 9; k++) os.ori[9 * pick + k] = mn[k];
+					}
+					tl.dbonds += b_new - b_old;
+					tl.acc++;
+					tl.wa += Wfix;
 				}
-				tl.dbonds += b_new - b_old;
-				tl.acc++;
-				tl.wa += Wfix;
+				else s_stage[j_self][tid] = self;
 			}
 			if(G > 1) __syncwarp(gmask); // the other lanes read the moved particle's new state in the next trials
 		}
@@ -386,7 +402,7 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 template<int G>
 __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
-		uint2 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
+		uint4 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
 	__shared__ __align__(16) CellSmem<G> sm;
 	sweep_cells_body<G>(sm, sc, range[0], range[1], (int) blockIdx.x, (int) gridDim.x, cell_start, work, proposals, pos, ori, posf, counters, hm);
 }
@@ -404,7 +420,7 @@ union FusedSmem {
 
 __global__ void __launch_bounds__(kCellThreads, 6) k_sweep_fused(const __grid_constant__ SimConst sc, const int *__restrict__ ranges /* 6 ints */,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
-		uint2 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
+		uint4 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
 	__shared__ __align__(16) unsigned char raw[sizeof(FusedSmem)];
 	const int b8 = ranges[0], e8 = ranges[1], b4 = ranges[2], e4 = ranges[3], b1 = ranges[4], e1 = ranges[5];
 	const int grid = (int) gridDim.x;

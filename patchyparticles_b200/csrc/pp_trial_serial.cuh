@@ -21,7 +21,7 @@ __device__ __forceinline__ int wrap_cell(int c, int n) {
 	return c;
 }
 
-static __device__ __noinline__ void trial_serial(const SimConst &sc, const int *__restrict__ cell_start, double4 *pos, double *ori, uint2 *posf,
+static __device__ __noinline__ void trial_serial(const SimConst &sc, const int *__restrict__ cell_start, double4 *pos, double *ori, uint4 *posf,
 		const Proposal *pr, int cell, int ix, int iy, int iz, int sp, Tally &tl, const HaloMirror &hm, int hm_off) {
 	const int ny = sc.n_side[1], nz = sc.n_side[2];
 	const double4 p4 = pos[sp];
@@ -79,8 +79,8 @@ static __device__ __noinline__ void trial_serial(const SimConst &sc, const int *
 		p[0] = p_new.x;
 		p[1] = p_new.y;
 		p[2] = p_new.z;
-		const uint2 moved = cell_shadow(sc, p_new.x, p_new.y, p_new.z, sp - cell_start[cell]);
-		posf[sp] = moved;
+		const uint4 moved = box_shadow(sc, p_new.x, p_new.y, p_new.z, sp);
+		store_shadow_xyz(posf + sp, moved);
 		for(int k = 0; k < 9; k++) ori[9ll * sp + k] = mn[k];
 		mirror_state(hm, hm_off, sp, p_new, moved, mn);
 		tl.dbonds += b_new - b_old;

@@ -209,9 +209,9 @@ class SlabEngine:
         sp, so, sf, ns = e.slab_halo(send_side, recv=False)
         rp, ro, rf, nr = e.slab_halo(1 - send_side, recv=True)
         send = [device_view(sp, 4 * ns, torch.float64, dev), device_view(so, 9 * ns, torch.float64, dev),
-                device_view(sf, 2 * ns, torch.int32, dev)]
+                device_view(sf, 4 * ns, torch.int32, dev)]
         recv = [device_view(rp, 4 * nr, torch.float64, dev), device_view(ro, 9 * nr, torch.float64, dev),
-                device_view(rf, 2 * nr, torch.int32, dev)]
+                device_view(rf, 4 * nr, torch.int32, dev)]
         return send, recv
 
     def _halo_refresh(self, send_side):

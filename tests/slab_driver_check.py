@@ -36,7 +36,7 @@ class StandInEngine:
         self.log = []
         self.layer = {}  # name -> (pos, ori, posf)
         for name, n in (("first", n_first(rank)), ("last", n_last(rank)), ("halo_l", n_last(self.left)), ("halo_r", n_first(self.right))):
-            self.layer[name] = (np.zeros(4 * n), np.zeros(9 * n), np.zeros(2 * n, dtype=np.int32))
+            self.layer[name] = (np.zeros(4 * n), np.zeros(9 * n), np.zeros(4 * n, dtype=np.int32))
         self.outbox, self.inbox = [None, None], [None, None]
         self.rebuilds = 0
 
@@ -82,7 +82,7 @@ class StandInEngine:
     def slab_halo(self, side, recv):
         name = (("halo_l", "halo_r") if recv else ("first", "last"))[side]
         pos, ori, posf = self.layer[name]
-        return pos.ctypes.data, ori.ctypes.data, posf.ctypes.data, len(posf) // 2
+        return pos.ctypes.data, ori.ctypes.data, posf.ctypes.data, len(posf) // 4
 
     def slab_sweep_end(self):
         self.log.append(("end", self.step))

@@ -1,17 +1,18 @@
-"""CPU check of the error budget behind the FP32 screens of the thread-per-cell sweep kernel
-(patchyparticles_b200/csrc/pp_sweep_cells.cu, pp_common.cuh: cell_shadow).
+"""CPU check of the error budget behind the FP32 screens of the sweep kernel and of the bond count
+(patchyparticles_b200/csrc/pp_sweep_cells.cu, pp_bonds.cu, pp_common.cuh: box_shadow / shadow_sep).
 
-The kernel never takes a decision in reduced precision, but it DISMISSES pairs from a 16-bit fixed-point
-shadow of the positions and FP32 arithmetic.  That is only safe while (a) the squared separation computed
-from the shadows is within the screen band of the exact one and (b) the orientation screen has no false
-negatives.  This file restates the shadow arithmetic in numpy (same quantisation, same operation order, FP32
-rounding after every operation the kernel rounds) and measures both on random configurations.  The GPU parity
-tests then show the kernel's decisions are the reference's; this test shows why, with the margin."""
+The kernels never take a decision in reduced precision, but they DISMISS pairs from a fixed-point shadow of
+the positions (every coordinate as a 32-bit fraction of the box side) and FP32 arithmetic.  That is only safe
+while (a) the squared separation computed from the shadows is within the screen band of the exact one and
+(b) the orientation screen has no false negatives.  This file restates the shadow arithmetic in numpy (same
+quantisation, same operation order, FP32 rounding after every operation the kernel rounds) and measures both on
+random configurations.  The GPU parity tests then show the kernel's decisions are the reference's; this test
+shows why, with the margin."""
 import numpy as np
 
 F = np.float32
 SCREEN_BAND = 2e-3          # kScreenBand
-CLAIMED_D2_ERROR = 2e-4
+CLAIMED_D2_ERROR = 1e-5     # DESIGN.md section 3 (boxes up to a few thousand diameters)
 
 
 def fma32(a, b, c):
@@ -19,15 +20,16 @@ def fma32(a, b, c):
     return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F)
 
 
-def shadow(frac_cells):
-    """cell_shadow: offset inside the cell in units of cell_w / 65535, rounded to nearest (16 bits)."""
-    return np.rint(frac_cells * 65535.0)
+def box_fraction(r, box):
+    """box_fraction: frac(r * (1 / box)) * 2^32 truncated to a 32-bit unsigned integer (saturating)."""
+    t = r * (1.0 / box)
+    f = t - np.floor(t)
+    return np.minimum(np.floor(f * 4294967296.0), 4294967295.0).astype(np.uint64).astype(np.uint32)
 
 
-def shadow_position(q, unit, off):
-    """shadow_position: fmaf(2^23 + q, unit, off - 2^23 * unit) with the bias rounded to FP32 once."""
-    bias = (off - 8388608.0 * unit.astype(np.float64)).astype(F)
-    return fma32((8388608.0 + q).astype(F), unit, bias)
+def shadow_sep(q, p, unit):
+    """shadow_sep: (float) (int) (q - p) * unit -- the wrapped difference IS the minimum image."""
+    return (((q - p).astype(np.uint32)).view(np.int32).astype(F) * unit).astype(F)
 
 
 def d2_f32(ax, ay, az):
@@ -45,27 +47,27 @@ def random_rotations(n, rng):
 
 def test_shadow_distance_error_within_band():
     rng = np.random.default_rng(1)
-    worst = 0.0
-    for cell_w in (1.119000002, 1.3, 1.678):  # smallest legal cell, a typical one, the largest (just below 1.5 r_cut)
+    for box_side, claimed in ((4.5, CLAIMED_D2_ERROR), (22.0, CLAIMED_D2_ERROR), (191.2, CLAIMED_D2_ERROR), (3000.0, CLAIMED_D2_ERROR), (40000.0, 2e-4)):
         n = 400000
-        w = np.full(3, cell_w)
-        unit = (w / 65535.0).astype(F)
-        # the moved particle in the home cell, a neighbour in one of the 27 cells around it, a displacement
-        fp, fq = rng.random((n, 3)), rng.random((n, 3))
-        code = rng.integers(-1, 2, size=(n, 3)).astype(np.float64)
+        box = np.array([box_side, box_side * 1.1, box_side * 0.93])
+        unit = (box / 4294967296.0).astype(F)
+        # the moved particle anywhere in the box (unwrapped coordinates, a few images away), a neighbour within range of
+        # it through the periodic boundary, a displacement
+        p_exact = (rng.random((n, 3)) * 5 - 2) * box
+        sep = rng.normal(size=(n, 3))
+        sep *= (rng.random(n) * 1.7 / np.linalg.norm(sep, axis=1))[:, None]
+        q_exact = p_exact + sep + rng.integers(-2, 3, size=(n, 3)) * box
         disp = (rng.random((n, 3)) - 0.5) * 0.3
-        p_exact, q_exact = fp * w, (fq + code) * w
-        keep = np.linalg.norm(q_exact - p_exact, axis=1) < 1.7  # what the screens are about
-        fo = np.stack([shadow_position(shadow(fp[:, k]), np.full(n, unit[k]), np.zeros(n)) for k in range(3)], axis=1)
-        qs = np.stack([shadow_position(shadow(fq[:, k]), np.full(n, unit[k]), code[:, k] * w[k]) for k in range(3)], axis=1)
-        fn = (fo + disp.astype(F)).astype(F)
-        a, b = (qs - fo).astype(F), (qs - fn).astype(F)
+        ps = np.stack([box_fraction(p_exact[:, k], box[k]) for k in range(3)], axis=1)
+        qs = np.stack([box_fraction(q_exact[:, k], box[k]) for k in range(3)], axis=1)
+        a = np.stack([shadow_sep(qs[:, k], ps[:, k], unit[k]) for k in range(3)], axis=1)
+        b = (a - disp.astype(F)).astype(F)
         d2o, d2n = d2_f32(a[:, 0], a[:, 1], a[:, 2]), d2_f32(b[:, 0], b[:, 1], b[:, 2])
-        eo = np.abs(d2o.astype(np.float64) - ((q_exact - p_exact) ** 2).sum(axis=1))
-        en = np.abs(d2n.astype(np.float64) - ((q_exact - p_exact - disp) ** 2).sum(axis=1))
-        worst = max(worst, eo[keep].max(), en[keep].max())
-    assert worst < CLAIMED_D2_ERROR, worst        # measured: ~1e-4 at the largest cell
-    assert worst < 0.1 * SCREEN_BAND + 1e-4      # an order of magnitude inside the band
+        eo = np.abs(d2o.astype(np.float64) - (sep ** 2).sum(axis=1))
+        en = np.abs(d2n.astype(np.float64) - ((sep - disp) ** 2).sum(axis=1))
+        worst = max(eo.max(), en.max())
+        assert worst < claimed, (box_side, worst)      # measured: ~1e-6 at 191, ~3e-6 at 3000, ~4e-5 at 40000
+        assert worst < 0.1 * SCREEN_BAND               # an order of magnitude inside the band
 
 
 def test_orientation_screen_has_no_false_negatives():
@@ -84,7 +86,7 @@ def test_orientation_screen_has_no_false_negatives():
     cos = np.einsum("nki,ni->nk", patches, dirs).max(axis=1)
     points = cos > cosmax                                                                  # exact, FP64
     # the screen: separation perturbed by the shadow error, FP32 matrix, FP32 arithmetic, 2e-3 relative band
-    d_f = (d + (rng.random((n, 3)) - 0.5) * 2 * 6e-5).astype(F)                           # worst-case shadow error per axis
+    d_f = (d + (rng.random((n, 3)) - 0.5) * 2 * 6e-5).astype(F)                           # far above the shadow error per axis
     mf = m.astype(F)
     d2 = d2_f32(d_f[:, 0], d_f[:, 1], d_f[:, 2])
     u = [fma32(mf[:, 2, k], d_f[:, 2], fma32(mf[:, 1, k], d_f[:, 1], (mf[:, 0, k] * d_f[:, 0]).astype(F))) for k in range(3)]
