@@ -62,7 +62,7 @@ typedef struct pp_params {
 	                               launch per colour pass in which sparsely populated cells run on one thread per cell, the middle
 	                               range on 4 lanes and the crowded cells on 8 lanes per cell; 1 = one thread per cell wherever a
 	                               cell fits it; 4, 8, 16, 32 = tile kernel of that width for every cell */
-	int cell_lanes;             /* 2, 4, 8: that many lanes per cell for the sparsely populated range (the three ranges then run as
+	int cell_lanes;             /* 2, 4, 8 (or -1: one thread): that many lanes per cell for the sparsely populated range (the three ranges then run as
 	                               three launches); 0 or 1: one thread per cell inside the fused launch */
 	int cells_max_occupancy;    /* cells with at most this many particles run on one thread per cell;
 	                               -1 = automatic (3 for N >= 800k, 2 for N >= 400k, 1 for N >= 150k, else 0), 0 = tile kernel only */

@@ -344,10 +344,10 @@ int launch_passes(pp_handle *h, const SimConst &sc, int first_pass, int n_pass) 
 		if(limit == 0) { // every cell on the tile kernel (the three ranges are contiguous: the first one holds everything)
 			nl += launch_sweep_pass(sc, ranges, lanes, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->hm, h->stream);
 		}
-		else if(cl == 2 || cl == 4 || cl == 8) { // an explicit lane count for the sparse range: the three configurations one after the other
+		else if(cl == 2 || cl == 4 || cl == 8 || cl == -1) { // an explicit lane count for the sparse range (-1: one thread per cell): the three configurations one after the other
 			nl += launch_sweep_cells(sc, ranges, n_active, 8, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->hm, h->stream);
 			nl += launch_sweep_cells(sc, ranges + 2, n_active, 4, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->hm, h->stream);
-			nl += launch_sweep_cells(sc, ranges + 4, n_active, cl, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->hm, h->stream);
+			nl += launch_sweep_cells(sc, ranges + 4, n_active, cl < 0 ? 1 : cl, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->hm, h->stream);
 		}
 		else nl += launch_sweep_fused(sc, ranges, n_active, h->cb, h->d_proposals, h->pos[h->cp], h->ori[h->co], h->d_counters, h->hm, h->stream);
 	}

@@ -150,13 +150,28 @@ __global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __
 			// neighbour minus own shadow, read as signed integers: the minimum-image separation in units of box / 2^32
 			const uint4 sh = posf[sp];
 			const float ux = (float) (sc.box[0] / 4294967296.), uy = (float) (sc.box[1] / 4294967296.), uz = (float) (sc.box[2] / 4294967296.);
-			const float thr = (float) sc.sqr_rcut + 2e-3f;
+			const float thr = (float) sc.sqr_rcut + 2e-3f, core_hi = 1.f + 2e-3f;
+			// orientation screen as in the sweep: a pair clear of the hard core can only bond if one of p's patches points at
+			// q; p's matrix is fetched (once per thread, in FP32) when the first pair in range turns up
+			const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - 2e-3f) : -1.f;
+			float mf[9];
+			bool have_m = false;
 #pragma unroll
 			for(int g = 0; g < 3; g++) {
 				for(int sq = sb[g]; sq < se[g]; sq++) {
 					const uint4 qh = posf[sq];
 					const float ax = shadow_sep(qh.x, sh.x, ux), ay = shadow_sep(qh.y, sh.y, uy), az = shadow_sep(qh.z, sh.z, uz);
-					if(fmaf(az, az, fmaf(ay, ay, ax * ax)) < thr) {
+					const float d2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+					if(d2 >= thr) continue;
+					if(d2 >= core_hi && point_thr >= 0.f) {
+						if(!have_m) {
+#pragma unroll
+							for(int k = 0; k < 9; k++) mf[k] = (float) ori[9ll * sp + k];
+							have_m = true;
+						}
+						if(!may_point(mf, ax, ay, az, d2, point_thr)) continue;
+					}
+					{
 						const int slot = atomicAdd(&s_queued[warp], 1);
 						if(slot < kQueue) s_queue[warp][slot] = make_int2(sp, sq);
 						else bond_pair_exact(sc, pos, ori, sp, sq, bonds, overlap); // (dense packings: more pairs than the queue holds)

@@ -152,6 +152,17 @@ __device__ __forceinline__ void store_shadow_xyz(uint4 *dst, const uint4 v) {
 // shadow separation -> FP32 separation: (float) (int) (q - p) * (box / 2^32)
 __device__ __forceinline__ float shadow_sep(unsigned q, unsigned p, float unit) { return (float) (int) (q - p) * unit; }
 
+// May one of the four patches of the particle with (FP32) matrix mf point at a neighbour at separation
+// (x, y, z), |.|^2 = d2 ?  d . (M b_i) = (M^T d) . b_i with b_i = (+-1, +-1, +-1) * base_z (system.c:23-31);
+// only the largest projection matters.  false means "certainly not" (see the band in the caller).
+__device__ __forceinline__ bool may_point(const float *mf, float x, float y, float z, float d2, float point_thr) {
+	const float ux = fmaf(mf[6], z, fmaf(mf[3], y, mf[0] * x));
+	const float uy = fmaf(mf[7], z, fmaf(mf[4], y, mf[1] * x));
+	const float uz = fmaf(mf[8], z, fmaf(mf[5], y, mf[2] * x));
+	const float pm = fmaxf(fmaxf(uz - ux - uy, ux - uy - uz), fmaxf(ux + uy + uz, uy - ux - uz));
+	return point_thr < 0.f || (pm > 0.f && pm * pm >= point_thr * d2);
+}
+
 // rint(d / box) as the reference computes it (MC.c:234-236), without the division in the common
 // case: rint(d * inv_box) can only differ from rint(d / box) when the quotient is within a couple
 // of ulps of a half-integer, and then the IEEE division is used.

@@ -38,17 +38,6 @@ constexpr int kCellThreads = 64;
 constexpr float kScreenBand = 2e-3f;         // safety band of the FP32 screens (error of the shadow arithmetic < 1e-5)
 constexpr unsigned kNearOld = 0x40u, kNearNew = 0x80u, kIdxMask = 0x3fu;
 
-// May one of the four patches of the particle with (FP32) matrix mf point at a neighbour at separation
-// (x, y, z), |.|^2 = d2 ?  d . (M b_i) = (M^T d) . b_i with b_i = (+-1, +-1, +-1) * base_z (system.c:23-31);
-// only the largest projection matters.  false means "certainly not" (see the band in the caller).
-__device__ __forceinline__ bool may_point(const float *mf, float x, float y, float z, float d2, float point_thr) {
-	const float ux = fmaf(mf[6], z, fmaf(mf[3], y, mf[0] * x));
-	const float uy = fmaf(mf[7], z, fmaf(mf[4], y, mf[1] * x));
-	const float uz = fmaf(mf[8], z, fmaf(mf[5], y, mf[2] * x));
-	const float pm = fmaxf(fmaxf(uz - ux - uy, ux - uy - uz), fmaxf(ux + uy + uz, uy - ux - uz));
-	return point_thr < 0.f || (pm > 0.f && pm * pm >= point_thr * d2);
-}
-
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct CellBlockCounters {
