@@ -412,10 +412,21 @@ int fetch_counters(pp_handle *h) {
 int count_bonds(pp_handle *h, int p, const double *box, const double *shift, long long *bonds, int *overlap) {
 	const SimConst sc = make_const(h, box, shift);
 	prof_begin(h);
-	const int nl = launch_total_bonds(sc, h->cb.cell_start, h->cb.cell_sorted, h->pos[p], h->ori[h->co], h->cb.posf, h->d_counters, h->stream);
+	// the proposals of a sweep are dead between sweeps: their buffer holds the pair queue of the streaming count
+	const size_t scratch_bytes = (size_t) h->cap_N * sizeof(Proposal);
+	const int nl = launch_total_bonds(sc, h->cb.cell_start, h->cb.cell_sorted, h->pos[p], h->ori[h->co], h->cb.posf, h->d_counters, h->d_proposals,
+			scratch_bytes, false, h->stream);
 	prof_end(h, PP_K_BONDS, nl);
 	CUDA_OK(h, cudaGetLastError());
 	if(fetch_counters(h)) return 1;
+	if(h->h_counters->pad != 0) { // more candidate pairs than the queue holds (a very dense, strongly bonded state): the exact tile kernel
+		prof_begin(h);
+		const int nt = launch_total_bonds(sc, h->cb.cell_start, h->cb.cell_sorted, h->pos[p], h->ori[h->co], h->cb.posf, h->d_counters, nullptr, 0, true,
+				h->stream);
+		prof_end(h, PP_K_BONDS, nt);
+		CUDA_OK(h, cudaGetLastError());
+		if(fetch_counters(h)) return 1;
+	}
 	*bonds = h->h_counters->bonds;
 	*overlap = h->h_counters->overlap;
 	return 0;

@@ -72,118 +72,202 @@ __global__ void __launch_bounds__(kBondThreads) k_total_bonds(const __grid_const
 __global__ void k_zero_bonds(Counters *counters) {
 	counters->bonds = 0;
 	counters->overlap = 0;
+	counters->pad = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3, streaming version (the default): one thread per (particle, column of the half shell).  Every unordered pair
-// is met once: the particle's own cell (slot_q > slot_p) and the 13 neighbour cells with (dx, dy, dz) > (0, 0, 0)
-// in lexicographic order, i.e. five columns -- (0, 0): the rest of the cell and the cell above it in z;
-// (0, +1), (+1, -1), (+1, 0), (+1, +1): three cells each.  Every candidate is first screened in FP32 from the
-// fixed-point shadows (box fractions; the same conservative screen as the sweep: squared distance below r_cut^2 + 2e-3,
-// shadow arithmetic good to 1e-5), so the FP64 position of a particle is fetched only for pairs that may be in
-// range and an orientation matrix only for a pair inside the bonding shell (p's side first; q's matrix only if
-// one of p's patches points at q, as the reference enters its inner loop, MC.c:249-255).  The global overlap
-// flag is polled by every thread: after the first overlap the rest returns at once, like the reference's
-// `while(!overlap_found)` loops (MC.c:488-495, 556-560).  Needs at least four cells per axis (the half shell
-// would meet a cell twice on an axis with two); smaller grids use the tile kernel above.
+// K3, streaming version (the default), two kernels.
+//
+// k_bonds_screen: one block per segment of a pencil of cells along z, one thread per particle.  Every unordered pair
+// is met once: the particle's own cell (slot_q > slot_p) and the 13 neighbour cells with (dx, dy, dz) > (0, 0, 0) in
+// lexicographic order, i.e. five columns -- (0, 0): the rest of the cell and the cell above it in z; (0, +1),
+// (+1, -1), (+1, 0), (+1, +1): three cells each.  With the linear cell index (ix ny + iy) nz + iz a column is ONE
+// contiguous run of slots, so the block brings the five runs it needs (its own z range plus one cell at either end; at
+// the ends of the box a copy of the periodic neighbour cell takes that place, so the three cells a particle looks at
+// are always contiguous in the staged run) into shared memory with coalesced 16-byte loads of the fixed-point
+// shadows, together with the cell bounds of those runs: two global round trips per block, everything after that is
+// served from shared memory.  A thread walks its particle's five ranges as one flat loop (the lanes of a warp then
+// differ by the spread of the neighbourhood size, not by the spread of each column).  Every candidate is screened in
+// FP32 from the shadows (box fractions; the same conservative screen as the sweep: squared distance below
+// r_cut^2 + 2e-3, shadow arithmetic good to 1e-5) and, clear of the hard core, by orientation: a bond needs one of
+// p's patches to point at q (MC.c:249-255), decided from p's matrix in FP32 through a relative band.  What survives
+// -- a few per cent of the pairs in range -- is appended to a pair queue in global memory (per-block queue in shared
+// memory, one global atomic per block).
+// k_bonds_exact: one thread per queued pair, the reference's FP64 arithmetic (MC.c:233-262), integer reduction.
+// No FP64 code, no orientation matrix and no FP64 position is touched by the screen: it runs at 40 registers.
+// The global overlap flag is polled by every block of both kernels: after the first overlap the rest returns at once,
+// like the reference's `while(!overlap_found)` loops (MC.c:488-495, 556-560).
+// Needs at least four cells per axis (the half shell would meet a cell twice on an axis with two); smaller grids
+// use the tile kernel above, and so does a configuration whose queue overflows (signalled through Counters.pad).
+// A run longer than the staging area (possible only in an overlapping configuration) is read from global memory
+// instead, same arithmetic.
 // A slab engine counts the pairs of its owned layers among themselves and with the right halo (dx = +1), never
 // with the left halo (dx = -1 is not in the half shell): every cross-boundary pair is counted once, on its left.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBondCellThreads = 256;
+constexpr int kPencilMaxThreads = 128;
+constexpr int kPencilMaxCells = 96;   // cells of a pencil per block
+constexpr int kPencilMaxCap = 288;    // staged shadows per column (hard spheres: < 2 per cell of side r_cut)
+constexpr int kPencilQueue = 512;     // queued pairs per block
 
-// FP64 pair test of (sp, sq) in the reference's operation order (MC.c:233-262) -> bond count, overlap
-static __device__ __noinline__ void bond_pair_exact(const SimConst &sc, const double4 *__restrict__ pos, const double *__restrict__ ori, int sp, int sq,
-		int &bonds, int &overlap) {
-	const double4 p4 = pos[sp];
-	const Vec3 p = {p4.x, p4.y, p4.z};
-	Vec3 d;
-	const double d2 = min_image(sc, p, pos[sq], d);
-	if(d2 < 1.) overlap = 1;
-	else if(d2 < sc.sqr_rcut) {
-		double m[9];
-#pragma unroll
-		for(int k = 0; k < 9; k++) m[k] = ori[9ll * sp + k];
-		bonds += patches_bond_m(sc, d, d2, m, ori + 9ll * sq) ? 1 : 0;
-	}
+// per column of the half shell: where its staged run comes from -- [copy of cell nz - 1][cells z_lo .. z_hi - 1][copy of cell 0]
+struct PencilColumn {
+	int g0, n_main;
+	int lw0, n_lw;
+	int hw0, n_hw;
+};
+
+__device__ __forceinline__ int pencil_slot(const PencilColumn &pc, int j) { // staged index -> slot
+	return j < pc.n_lw ? pc.lw0 + j : (j < pc.n_lw + pc.n_main ? pc.g0 + (j - pc.n_lw) : pc.hw0 + (j - pc.n_lw - pc.n_main));
 }
 
-__global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
-		const int *__restrict__ cell_sorted, const double4 *__restrict__ pos, const double *__restrict__ ori, const uint4 *__restrict__ posf,
-		Counters *counters) {
-	// pairs that pass the FP32 screen are queued per warp and tested in FP64 by all its lanes together: the exact test is
-	// a few hundred instructions, and taken where it is found it would run with one or two lanes of the warp active
-	constexpr int kQueue = 96;
-	__shared__ int2 s_queue[kBondCellThreads / 32][kQueue];
-	__shared__ int s_queued[kBondCellThreads / 32];
-	__shared__ int s_bonds, s_overlap;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	if(threadIdx.x == 0) {
-		s_bonds = 0;
-		s_overlap = 0;
+__global__ void __launch_bounds__(kPencilMaxThreads, 8) k_bonds_screen(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
+		const int *__restrict__ cell_sorted, const double *__restrict__ ori, const uint4 *__restrict__ posf, const Counters *counters, int2 *queue,
+		const int queue_cap, const int seg_cells, const int n_seg, const int cap) {
+	constexpr int kRow = kPencilMaxCells + 3;
+	extern __shared__ __align__(16) unsigned char s_raw[];
+	__shared__ PencilColumn s_col[5];
+	__shared__ int s_nq, s_qbase;
+	if(*((volatile const int *) &counters->overlap) != 0) return;
+	const int tid = threadIdx.x;
+	const int ny = sc.n_side[1], nz = sc.n_side[2];
+	const int pencil = (int) blockIdx.x / n_seg, seg = (int) blockIdx.x - pencil * n_seg;
+	const int ix = sc.own_lo + pencil / ny, iy = pencil - (pencil / ny) * ny;
+	const int z0 = seg * seg_cells, z1 = min(z0 + seg_cells, nz); // own cells [z0, z1)
+	const int nk = z1 - z0 + 2;                                    // window cell k <-> cell z0 - 1 + k (periodic)
+	const int z_lo = max(z0 - 1, 0), z_hi = min(z1 + 1, nz);
+	uint4 *s_stage = reinterpret_cast<uint4 *>(s_raw);                              // [5][cap]
+	int2 *s_q = reinterpret_cast<int2 *>(s_raw + sizeof(uint4) * 5 * cap);          // [kPencilQueue]
+	int *s_beg = reinterpret_cast<int *>(s_q + kPencilQueue);                       // [5][kRow]: staged index of the first member of window cell k (k = nk: the end)
+	if(tid == 0) s_nq = 0;
+
+	// ---- cell bounds of the five columns ------------------------------------------------------------------------
+	for(int i = tid; i < 5 * (nk + 1); i += blockDim.x) {
+		const int c = i / (nk + 1), k = i - c * (nk + 1);
+		const int dx = c >= 2, dy = c == 0 ? 0 : (c == 1 ? 1 : c - 3);
+		int cx = ix + dx;
+		if(!sc.slab) cx -= (cx >= sc.nxl) ? sc.nxl : 0; // (slab: an owned layer always has its +x neighbour in the held range)
+		int cy = iy + dy;
+		cy += (cy < 0) ? ny : 0;
+		cy -= (cy >= ny) ? ny : 0;
+		const int *cs = cell_start + (cx * ny + cy) * nz;
+		PencilColumn pc;
+		pc.g0 = cs[z_lo];
+		pc.n_main = cs[z_hi] - pc.g0;
+		pc.lw0 = cs[nz - 1];
+		pc.n_lw = z0 == 0 ? cs[nz] - pc.lw0 : 0;
+		pc.hw0 = cs[0];
+		pc.n_hw = z1 == nz ? cs[1] - pc.hw0 : 0;
+		const int z = z0 - 1 + k; // k = nk: one past the last window cell
+		int at;
+		if(z < 0) at = 0;
+		else if(z < z_hi) at = pc.n_lw + (cs[z] - pc.g0);
+		else if(z == z_hi) at = pc.n_lw + pc.n_main;
+		else at = pc.n_lw + pc.n_main + pc.n_hw;
+		s_beg[c * kRow + k] = at;
+		if(k == 0) s_col[c] = pc;
 	}
-	if(lane == 0) s_queued[warp] = 0;
 	__syncthreads();
-	const int ny = sc.n_side[1], nz = sc.n_side[2], nyz = ny * nz;
-	int bonds = 0, overlap = 0;
-	const long long t = (long long) blockIdx.x * kBondCellThreads + threadIdx.x;
-	const int sp = (int) (t / 5), col = (int) (t - 5ll * sp);
-	if(sp < sc.N && *((volatile int *) &counters->overlap) == 0) {
-		const int cell = cell_sorted[sp];
-		const int ix = cell / nyz, iy = (cell - ix * nyz) / nz, iz = cell - ix * nyz - iy * nz;
-		if(cell < sc.n_cells && ix >= sc.own_lo && ix < sc.own_hi) {
-			const int dx = col >= 2, dy = col == 0 ? 0 : (col == 1 ? 1 : col - 3);
-			int cx = ix + dx;
-			if(!sc.slab) cx -= (cx >= sc.nxl) ? sc.nxl : 0; // (slab: an owned layer always has its +x neighbour in the held range)
-			int cy = iy + dy;
-			cy += (cy < 0) ? ny : 0;
-			cy -= (cy >= ny) ? ny : 0;
-			const int *cs = cell_start + (cx * ny + cy) * nz;
-			const int zm = iz > 0 ? iz - 1 : nz - 1, zp = iz < nz - 1 ? iz + 1 : 0;
-			// three segments (dz = -1, 0, +1); column 0 has no dz = -1 cell and starts its own cell after the particle itself
-			int sb[3], se[3];
-			sb[0] = col ? cs[zm] : 0;
-			se[0] = col ? cs[zm + 1] : 0;
-			sb[1] = col ? cs[iz] : sp + 1;
-			se[1] = cs[iz + 1];
-			sb[2] = cs[zp];
-			se[2] = cs[zp + 1];
-			// neighbour minus own shadow, read as signed integers: the minimum-image separation in units of box / 2^32
-			const uint4 sh = posf[sp];
-			const float ux = (float) (sc.box[0] / 4294967296.), uy = (float) (sc.box[1] / 4294967296.), uz = (float) (sc.box[2] / 4294967296.);
-			const float thr = (float) sc.sqr_rcut + 2e-3f, core_hi = 1.f + 2e-3f;
-			// orientation screen as in the sweep: a pair clear of the hard core can only bond if one of p's patches points at
-			// q; p's matrix is fetched (once per thread, in FP32) when the first pair in range turns up
-			const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - 2e-3f) : -1.f;
+	bool fits = true;
+#pragma unroll
+	for(int c = 0; c < 5; c++) fits &= s_col[c].n_main + s_col[c].n_lw + s_col[c].n_hw <= cap;
+
+	// ---- the five runs of shadows ---------------------------------------------------------------------------------
+	if(fits) {
+#pragma unroll 1
+		for(int c = 0; c < 5; c++) {
+			const PencilColumn pc = s_col[c];
+			const int total = pc.n_main + pc.n_lw + pc.n_hw;
+			for(int i = tid; i < total; i += blockDim.x) s_stage[c * cap + i] = posf[pencil_slot(pc, i)];
+		}
+	}
+	__syncthreads();
+
+	const float ux = (float) (sc.box[0] / 4294967296.), uy = (float) (sc.box[1] / 4294967296.), uz = (float) (sc.box[2] / 4294967296.);
+	const float thr = (float) sc.sqr_rcut + 2e-3f, core_hi = 1.f + 2e-3f;
+	const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - 2e-3f) : -1.f;
+	const PencilColumn own = s_col[0];
+	const int *cs_own = cell_start + (ix * ny + iy) * nz;
+	const int own_first = cs_own[z0], n_own = cs_own[z1] - own_first;
+	for(int base = 0; base < n_own; base += blockDim.x) {
+		const int sp = own_first + base + tid;
+		if(base + tid < n_own) {
+			const int k_own = cell_sorted[sp] % nz - z0 + 1;
+			const int j_own = own.n_lw + (sp - own.g0); // staged index of the particle itself (column 0)
+			const uint4 sh = fits ? s_stage[j_own] : posf[sp];
 			float mf[9];
 			bool have_m = false;
+			// the five ranges as one loop: column 0 from the particle itself to the end of the cell above, the others three cells
+			int c = 0, j = j_own + 1, e = s_beg[k_own + 2];
+			while(true) {
+				while(j >= e && c < 4) {
+					c++;
+					j = s_beg[c * kRow + k_own - 1];
+					e = s_beg[c * kRow + k_own + 2];
+				}
+				if(j >= e) break;
+				const uint4 qh = fits ? s_stage[c * cap + j] : posf[pencil_slot(s_col[c], j)];
+				j++;
+				const float ax = shadow_sep(qh.x, sh.x, ux), ay = shadow_sep(qh.y, sh.y, uy), az = shadow_sep(qh.z, sh.z, uz);
+				const float d2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
+				if(d2 >= thr) continue;
+				if(d2 >= core_hi && point_thr >= 0.f) {
+					if(!have_m) {
 #pragma unroll
-			for(int g = 0; g < 3; g++) {
-				for(int sq = sb[g]; sq < se[g]; sq++) {
-					const uint4 qh = posf[sq];
-					const float ax = shadow_sep(qh.x, sh.x, ux), ay = shadow_sep(qh.y, sh.y, uy), az = shadow_sep(qh.z, sh.z, uz);
-					const float d2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
-					if(d2 >= thr) continue;
-					if(d2 >= core_hi && point_thr >= 0.f) {
-						if(!have_m) {
-#pragma unroll
-							for(int k = 0; k < 9; k++) mf[k] = (float) ori[9ll * sp + k];
-							have_m = true;
-						}
-						if(!may_point(mf, ax, ay, az, d2, point_thr)) continue;
+						for(int k = 0; k < 9; k++) mf[k] = (float) ori[9ll * sp + k];
+						have_m = true;
 					}
-					{
-						const int slot = atomicAdd(&s_queued[warp], 1);
-						if(slot < kQueue) s_queue[warp][slot] = make_int2(sp, sq);
-						else bond_pair_exact(sc, pos, ori, sp, sq, bonds, overlap); // (dense packings: more pairs than the queue holds)
-					}
+					if(!may_point(mf, ax, ay, az, d2, point_thr)) continue;
+				}
+				const int2 pair = make_int2(sp, (int) qh.w); // the shadow carries its slot
+				const int slot = atomicAdd(&s_nq, 1);
+				if(slot < kPencilQueue) s_q[slot] = pair;
+				else { // (more pairs than the block's queue holds: straight to the global queue)
+					const int g = atomicAdd(&queue[0].x, 1);
+					if(g < queue_cap) queue[1 + g] = pair;
+					else queue[0].y = 1;
 				}
 			}
 		}
 	}
-	__syncwarp();
-	{
-		const int n = min(s_queued[warp], kQueue);
-		for(int i = lane; i < n; i += 32) bond_pair_exact(sc, pos, ori, s_queue[warp][i].x, s_queue[warp][i].y, bonds, overlap);
+	__syncthreads();
+	const int n = min(s_nq, kPencilQueue);
+	if(n == 0) return;
+	if(tid == 0) s_qbase = atomicAdd(&queue[0].x, n);
+	__syncthreads();
+	const int gb = s_qbase;
+	for(int i = tid; i < n; i += blockDim.x) {
+		if(gb + i < queue_cap) queue[1 + gb + i] = s_q[i];
+		else queue[0].y = 1;
+	}
+}
+
+// FP64 pair test of the queued pairs in the reference's operation order (MC.c:233-262) -> bond count, overlap
+__global__ void __launch_bounds__(128) k_bonds_exact(const __grid_constant__ SimConst sc, const double4 *__restrict__ pos, const double *__restrict__ ori,
+		const int2 *__restrict__ queue, const int queue_cap, Counters *counters) {
+	__shared__ int s_bonds, s_overlap;
+	if(threadIdx.x == 0) {
+		s_bonds = 0;
+		s_overlap = 0;
+	}
+	__syncthreads();
+	const int2 head = queue[0];
+	if(head.y != 0 && blockIdx.x == 0 && threadIdx.x == 0) counters->pad = 1; // queue overflow: the host repeats the count with the tile kernel
+	const int n = min(head.x, queue_cap);
+	int bonds = 0, overlap = 0;
+	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		if(*((volatile int *) &counters->overlap) != 0) break;
+		const int2 pr = queue[1 + i];
+		const double4 p4 = pos[pr.x];
+		const Vec3 p = {p4.x, p4.y, p4.z};
+		Vec3 d;
+		const double d2 = min_image(sc, p, pos[pr.y], d);
+		if(d2 < 1.) overlap = 1;
+		else if(d2 < sc.sqr_rcut) {
+			double m[9];
+#pragma unroll
+			for(int k = 0; k < 9; k++) m[k] = ori[9ll * pr.x + k];
+			bonds += patches_bond_m(sc, d, d2, m, ori + 9ll * pr.y) ? 1 : 0;
+		}
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
@@ -201,16 +285,41 @@ __global__ void __launch_bounds__(kBondCellThreads) k_total_bonds_cells(const __
 	}
 }
 
+__global__ void k_zero_bonds_queue(Counters *counters, int2 *queue) {
+	counters->bonds = 0;
+	counters->overlap = 0;
+	counters->pad = 0;
+	queue[0] = make_int2(0, 0);
+}
+
+// scratch: device buffer of scratch_bytes the pair queue may use (nullptr: tile kernel); force_tile: the exact tile kernel whatever the grid
 int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint4 *posf,
-		Counters *counters, cudaStream_t st) {
-	k_zero_bonds<<<1, 1, 0, st>>>(counters);
+		Counters *counters, void *scratch, size_t scratch_bytes, bool force_tile, cudaStream_t st) {
 	const bool wide = (sc.slab || sc.nxl >= 4) && sc.n_side[1] >= 4 && sc.n_side[2] >= 4;
-	if(wide && posf != nullptr && sc.N > 0) {
-		const long long threads = 5ll * sc.N;
-		k_total_bonds_cells<<<(unsigned) ((threads + kBondCellThreads - 1) / kBondCellThreads), kBondCellThreads, 0, st>>>(sc, cell_start, cell_sorted, pos,
-				ori, posf, counters);
-		return 2;
+	if(wide && !force_tile && posf != nullptr && scratch != nullptr && scratch_bytes >= 4096 && sc.N > 0) {
+		int2 *queue = reinterpret_cast<int2 *>(scratch);
+		const long long qcap = (long long) (scratch_bytes / sizeof(int2)) - 1;
+		const int queue_cap = qcap > 0x3fffffffll ? 0x3fffffff : (int) qcap;
+		k_zero_bonds_queue<<<1, 1, 0, st>>>(counters, queue);
+		const int nz = sc.n_side[2];
+		const int n_seg = (nz + kPencilMaxCells - 1) / kPencilMaxCells, seg_cells = (nz + n_seg - 1) / n_seg;
+		const long long n_pencils = (long long) (sc.own_hi - sc.own_lo) * sc.n_side[1];
+		// staging area per column: twice the mean population of the window at one particle per cell (a hard-sphere
+		// packing holds fewer than two per cell of side r_cut; cells of a small box are wider, the window is shorter)
+		const double occ = (double) sc.N / ((double) sc.n_cells > 0. ? (double) sc.n_cells : 1.);
+		int cap = (int) ((seg_cells + 4) * (occ > 1. ? 2. * occ : 2.)) + 16;
+		if(cap > kPencilMaxCap) cap = kPencilMaxCap;
+		const double own = occ * seg_cells; // particles of a block
+		const int threads = own <= 24. ? 32 : (own <= 56. ? 64 : kPencilMaxThreads);
+		const size_t smem = sizeof(uint4) * 5 * cap + sizeof(int2) * kPencilQueue + sizeof(int) * 5 * (kPencilMaxCells + 3);
+		k_bonds_screen<<<(unsigned) (n_pencils * n_seg), threads, smem, st>>>(sc, cell_start, cell_sorted, ori, posf, counters, queue, queue_cap, seg_cells,
+				n_seg, cap);
+		long long est = (long long) sc.N / 2 + 128; // pairs expected in the queue at most in a fluid; the kernel strides over whatever is there
+		int blocks = (int) ((est + 127) / 128 > 148 * 8 ? 148 * 8 : (est + 127) / 128);
+		k_bonds_exact<<<blocks, 128, 0, st>>>(sc, pos, ori, queue, queue_cap, counters);
+		return 3;
 	}
+	k_zero_bonds<<<1, 1, 0, st>>>(counters);
 	constexpr int G = 8;
 	const int tiles_per_block = kBondThreads / G;
 	int blocks = (sc.n_cells + tiles_per_block - 1) / tiles_per_block;

@@ -136,7 +136,11 @@ __device__ __forceinline__ int neighbourhood_total(const SimConst &sc, const int
 __device__ __forceinline__ int work_bin(const SimConst &sc, int ix, int iy, int iz, int n, bool dense, int nb_total) {
 	const int colour = ((ix + sc.x_lo) & 1) | ((iy & 1) << 1) | ((iz & 1) << 2); // parity of the GLOBAL layer
 	const int bucket = (dense || n >= kWorkBuckets) ? kWorkBuckets : n;            // 1 .. kWorkBuckets
-	const int cls = nb_total > 0 ? min((nb_total - 1) >> 2, kWorkSub - 1) : 0;      // staged entries rounded up to four, in fours
+	// staged entries rounded up to four, in fours (classes 1 .. kWorkSub - 1); class 0 collects the cells of the first and last z
+	// layer, whose neighbourhood wraps around the box: the sweep kernel stages those with an extra loop, which then runs in a few
+	// warps full of such cells instead of one lane of every other warp
+	const bool edge = iz == 0 || iz == sc.n_side[2] - 1;
+	const int cls = edge ? 0 : 1 + (nb_total > 0 ? min((nb_total - 1) >> 2, kWorkSub - 2) : 0);
 	return (colour * kWorkBuckets + (kWorkBuckets - bucket)) * kWorkSub + (kWorkSub - 1 - cls); // big cells first, big neighbourhoods first
 }
 

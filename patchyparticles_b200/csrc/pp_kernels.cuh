@@ -79,8 +79,10 @@ int launch_sweep_fused(const SimConst &sc, const int *ranges, long long max_item
 
 // K3: full bond count + overlap flag into counters->bonds / counters->overlap (zeroed by the launcher)
 // (posf: the shadows of the same slots; nullptr or a grid with fewer than four cells on an axis: the tile kernel without the FP32 screen)
+// scratch: device memory for the queue of pairs that pass the FP32 screens (nullptr: tile kernel); a queue overflow is reported in
+// counters->pad and the caller repeats the count with force_tile
 int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cell_sorted, const double4 *pos, const double *ori, const uint4 *posf,
-		Counters *counters, cudaStream_t st);
+		Counters *counters, void *scratch, size_t scratch_bytes, bool force_tile, cudaStream_t st);
 // per-particle bonded-neighbour counts (indexed by particle id)
 int launch_bond_counts(const SimConst &sc, const int *cell_start, const double4 *pos, const double *ori, const int *pid, int *counts, int *neighbours,
 		int max_nb, cudaStream_t st);

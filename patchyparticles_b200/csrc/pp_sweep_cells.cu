@@ -281,9 +281,20 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 					const float bx = ax - fdx, by = ay - fdy, bz = az - fdz;
 					const float d2o = fmaf(az, az, fmaf(ay, ay, ax * ax));
 					const float d2n = fmaf(bz, bz, fmaf(by, by, bx * bx));
-					unsigned keep = 0u;
-					if(d2n < thr && (d2n < core_hi || may_point(mnf, bx, by, bz, d2n, point_thr))) keep |= kNearNew;
-					if(d2o < thr && may_point(mf, ax, ay, az, d2o, point_thr)) keep |= kNearOld;
+					const bool core_new = d2n < core_hi; // (d2n < thr as well) the hard core is decided in FP64 whatever the patches do
+					bool pt_new = d2n < thr && !core_new && may_point(mnf, bx, by, bz, d2n, point_thr);
+					bool pt_old = d2o < thr && may_point(mf, ax, ay, az, d2o, point_thr);
+					if((pt_new || pt_old) && point_thr >= 0.f) {
+						// ... and one of the neighbour's patches to point back (MC.c:256-259): the same screen from the neighbour's
+						// matrix, which the FP64 test would fetch anyway; 96 % of what came this far ends here
+						float mq[9];
+						const double *oq = ori + 9ll * (int) q.w;
+#pragma unroll
+						for(int k = 0; k < 9; k++) mq[k] = (float) oq[k];
+						pt_new = pt_new && may_point(mq, -bx, -by, -bz, d2n, point_thr);
+						pt_old = pt_old && may_point(mq, -ax, -ay, -az, d2o, point_thr);
+					}
+					const unsigned keep = ((core_new || pt_new) ? kNearNew : 0u) | (pt_old ? kNearOld : 0u);
 					if(keep) s_cand[n_exact++][tid] = (unsigned char) (j | keep); // in place: n_exact <= c0
 				}
 			}

@@ -220,3 +220,34 @@ def test_npt_statistics_vs_reference(tmp_path):
     assert 0.35 < r_ref < 0.45
     assert abs(r_gpu - r_ref) < 3.0 * np.hypot(sr_ref, sr_gpu)
     assert abs(a_gpu - a_ref) < 3.0 * np.hypot(sa_ref, sa_gpu)
+
+
+
+def test_lx_statistics_vs_reference(tmp_path):
+    """NVT with Lx_move = 1 (MC.c:515-585, scheduled at MC.c:25): mean and spread of Lx from boxshape.dat, the Lx-move
+    acceptance and <E>/N at a bonded state point (so the exp(+dE/T) sign of MC.c:562 is part of what is compared).  N = 300
+    at rho = 0.25 with the y/z side held in [10.45, 10.8]: Lx then decorrelates within a few hundred steps (measured with
+    tools/lx_probe.py: autocorrelation 0.2 at 250 steps), so ten blocks of 3700 steps give honest error bars."""
+    need_binaries()
+    keys = dict(Temperature=0.3, Lx_move=1, Lx_change_max=0.4, Lyz_min=10.45, Lyz_max=10.8, Print_every=50)
+    d_ref, d_gpu = make_case(tmp_path, 300, 0.25, Steps=40000, **keys)
+    run(REF_BIN, d_ref)
+    run(HOST_BIN, d_gpu)
+    discard = 3000
+    res = {}
+    for tag, d in (("ref", d_ref), ("gpu", d_gpu)):
+        b = load_cols(d / "boxshape.dat")
+        a = load_cols(d / "acceptance.dat")
+        e = load_cols(d / "energy.dat")
+        assert b.shape[1] == 4 and a.shape[1] == 3  # step Lx Ly Lz; step, roto, Lx
+        b = b[b[:, 0] >= discard]
+        assert np.allclose(b[:, 1] * b[:, 2] * b[:, 3], b[0, 1] * b[0, 2] * b[0, 3], rtol=1e-5)  # the move keeps V (MC.c:521)
+        assert np.all(b[:, 2] > 10.45 - 1e-6) and np.all(b[:, 2] < 10.8 + 1e-6)
+        acc = a[a[:, 0] >= discard, 2]
+        res[tag] = (block_stats(b[:, 1]), block_stats((b[:, 1] - b[:, 1].mean()) ** 2), block_stats(acc[np.isfinite(acc)]),
+                    block_stats(e[e[:, 0] >= discard, 1]))
+    for name, k, lo, hi in (("<Lx>", 0, 10.3, 10.95), ("var Lx", 1, 0.02, 0.06), ("Lx acceptance", 2, 0.1, 0.5), ("E/N", 3, -0.4, -0.05)):
+        (m_ref, s_ref), (m_gpu, s_gpu) = res["ref"][k], res["gpu"][k]
+        print(f"{name}: ref {m_ref:.4f} +- {s_ref:.4f}   gpu {m_gpu:.4f} +- {s_gpu:.4f}")
+        assert lo < m_ref < hi
+        assert abs(m_gpu - m_ref) < 3.0 * np.hypot(s_ref, s_gpu), name
