@@ -449,17 +449,20 @@ def measure(pkg, args, w, K, W, n_e2e, cpu_budget_s, ctx, headline):
     peak, peak_src = measured_peaks()
     sweep_launches, sweep_ms = stats["sweep"]
     n_passes = 8 * n_prof
-    per_pass_ms = sweep_ms / n_passes
+    passes_per_launch = max(int(round(n_passes / max(sweep_launches, 1))), 1)  # 1: a launch per colour pass; 4: a dataflow launch per half sweep
+    per_launch_ms = sweep_ms / max(sweep_launches, 1)
     tile_only = (n_local < 150000 and args.cells_max_occupancy < 0 and args.lanes != 1) or min(cells) < 4
-    sweep_kernel = "k_sweep_pass (tile kernel)" if tile_only else "k_sweep_fused (8 / 4 / 1 lanes per cell in one launch)"
+    sweep_kernel = ("k_sweep_pass (tile kernel)" if tile_only else
+                    "k_sweep_half (the four colour passes of a half sweep in one dataflow launch; 8 / 4 / 1 lanes per cell)" if passes_per_launch == 4 else
+                    "k_sweep_fused (8 / 4 / 1 lanes per cell in one launch)")
     n_owned = N / world if sharded else N
-    bytes_per_launch = SWEEP_BYTES_PER_ATTEMPT * n_owned / 8.0
-    achieved = bytes_per_launch / (per_pass_ms * 1e-3) / 1e9
+    bytes_per_launch = SWEEP_BYTES_PER_ATTEMPT * n_owned * passes_per_launch / 8.0
+    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     cell_builds = max(stats["cells"][0] // 10, 1)
     n_bonds = max(stats["bonds"][0], 1)
     kernels = {
-        "sweep_pass": {"launches": sweep_launches, "passes": n_passes, "ms_per_launch": per_pass_ms, "alg_bytes_per_launch": bytes_per_launch,
-                       "GBps": achieved},
+        "sweep_pass": {"launches": sweep_launches, "passes": n_passes, "ms_per_launch": per_launch_ms, "ms_per_pass": sweep_ms / n_passes,
+                       "alg_bytes_per_launch": bytes_per_launch, "GBps": achieved},
         "cell_build": {"launches": stats["cells"][0], "builds": cell_builds, "ms_per_build": stats["cells"][1] / cell_builds,
                        "GBps": CELLS_BYTES_PER_PARTICLE * n_local / (max(stats["cells"][1], 1e-9) / cell_builds * 1e-3) / 1e9},
         "proposals": {"launches": stats["rng"][0], "ms_per_launch": stats["rng"][1] / max(stats["rng"][0], 1)},

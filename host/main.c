@@ -43,6 +43,8 @@ typedef struct {
 	int *bond_counts, *bond_neighbours;
 } host_output;
 
+#define PP_HOST_GC 1  /* Ensemble values the host itself drives (defs.h:22-23) */
+#define PP_HOST_SUS 3
 #define PP_HOST_MAX_BONDS 16 /* neighbours listed per particle; four patches of half-angle acos(0.98) hold far fewer */
 
 static void log_msg(host_output *out, const char *fmt, ...) {
@@ -117,14 +119,14 @@ static void print_bonds(host_output *out, pp_group *h, int N, llint step) {
 	fclose(f);
 }
 
-static void print_observables(host_output *out, pp_group *h, const pp_params *prm, llint step) {
+static void print_observables(host_output *out, pp_group *h, const pp_params *prm, int ensemble, llint step) {
 	pp_observables o;
 	PP_CALL(out, h, pp_group_get_observables(h, &o, 1)); /* counters are reset after each print (output.c:189) */
 	const double V = o.volume; /* System.V, output.c:131 */
 	const double E = (o.N > 0) ? o.energy / o.N : 0.;
 	fprintf(out->energy, "%lld %lf\n", step, E);
 	fflush(out->energy);
-	if(prm->ensemble != PP_NVT) {
+	if(ensemble != PP_NVT) {
 		fprintf(out->density, "%lld %lf %d\n", step, o.N / V, o.N);
 		fflush(out->density);
 	}
@@ -137,12 +139,16 @@ static void print_observables(host_output *out, pp_group *h, const pp_params *pr
 	const double zero = 0.;
 	const double acc_roto = (o.tries[PP_ROTO_TRASL] > 0) ? o.acceptance_roto : zero / zero;
 	fprintf(out->acc, "%lld %e", step, acc_roto);
+	if(ensemble == PP_HOST_GC || ensemble == PP_HOST_SUS) { /* output.c:166-170 */
+		fprintf(out->acc, " %e", o.accepted[PP_ADD] / (double) o.tries[PP_ADD]);
+		fprintf(out->acc, " %e", o.accepted[PP_REMOVE] / (double) o.tries[PP_REMOVE]);
+	}
 	if(prm->ensemble == PP_NPT) fprintf(out->acc, " %e", o.accepted[PP_VOLUME] / (double) o.tries[PP_VOLUME]);
 	if(prm->Lx_move) fprintf(out->acc, " %e", o.accepted[PP_LX] / (double) o.tries[PP_LX]);
 	fprintf(out->acc, "\n");
 	fflush(out->acc);
 	printf("%lld %lf %lf", step, E, o.energy);
-	if(prm->ensemble != PP_NVT) printf(" %lf", o.N / V);
+	if(ensemble != PP_NVT) printf(" %lf", o.N / V);
 	printf("\n");
 	fflush(stdout);
 }
@@ -217,9 +223,28 @@ int main(int argc, char *argv[]) {
 		if(access(out.bonds_folder, W_OK) != 0)
 			die(&out, "Cannot create files in directory '%s': please make sure that the directory exists and it is writable\n", out.bonds_folder);
 	}
-	if(prm.ensemble != PP_NVT && prm.ensemble != PP_NPT)
-		die(&out, "Ensemble %d not supported on the GPU path (0 = NVT, 5 = NPT; GC/SUS/BSUS stay on the CPU reference)\n", prm.ensemble);
-	if(prm.ensemble != PP_NVT) {
+	/* Ensemble = 1 (GC) / 3 (SUS), system.c:90-103: insertions and removals (MC_add_remove, MC.c:342-448) are driven from here,
+	 * pp_gc_step before every sweep; the engine itself runs its NVT sweeps */
+	const int ensemble = prm.ensemble;
+	double activity = 0.;
+	int n_min = 0, n_max = 0;
+	llint *sus_hist = NULL;
+	char sus_folder[512] = "";
+	if(ensemble == PP_HOST_GC || ensemble == PP_HOST_SUS) {
+		pph_get_double(in, "Activity", &activity, 1);
+		if(ensemble == PP_HOST_GC) pph_get_int(in, "GC_N_max", &n_max, 1);
+		else {
+			pph_get_int(in, "Umbrella_sampling_min", &n_min, 1);
+			pph_get_int(in, "Umbrella_sampling_max", &n_max, 1);
+			pph_get_string(in, "Umbrella_sampling_folder", sus_folder, sizeof(sus_folder), 1);
+			if(access(sus_folder, W_OK) != 0)
+				die(&out, "Cannot create files in directory '%s': please make sure that the directory exists and it is writable\n", sus_folder);
+		}
+		prm.ensemble = PP_NVT;
+	}
+	else if(prm.ensemble != PP_NVT && prm.ensemble != PP_NPT)
+		die(&out, "Ensemble %d not supported on the GPU path (0 = NVT, 1 = GC, 3 = SUS, 5 = NPT; BSUS stays on the CPU reference)\n", prm.ensemble);
+	if(ensemble != PP_NVT) {
 		snprintf(name, sizeof(name), "density.dat");
 		pph_get_string(in, "Density_file", name, sizeof(name), 0);
 		out.density = open_or_die(&out, name, mode, "Density");
@@ -233,6 +258,19 @@ int main(int argc, char *argv[]) {
 	if(rc == -2) die(&out, "The initial configuration file '%s' is empty or its headers are malformed\n", conf_name);
 	if(rc == -3) die(&out, "Number of particles found in configuration (%d) is different from the value found in the header (%d)\n", found, N);
 	out.start_from = restart_step_counter ? 0 : conf_step;
+	if(ensemble == PP_HOST_GC || ensemble == PP_HOST_SUS) {
+		if(ensemble == PP_HOST_SUS) { /* system.c:100-102 */
+			if(N < n_min) die(&out, "Number of particles %d is smaller than Umbrella_sampling_min (%d)\n", N, n_min);
+			if(N > n_max) die(&out, "Number of particles %d is larger than Umbrella_sampling_max (%d)\n", N, n_max);
+			sus_hist = calloc((size_t) (n_max - n_min + 1), sizeof(llint));
+			if(sus_hist == NULL) die(&out, "out of memory\n");
+		}
+		if(n_max < N) die(&out, "The initial configuration holds %d particles, more than the maximum of %d\n", N, n_max);
+		double *r2 = realloc(r, sizeof(double) * 3 * (size_t) (n_max + 1)), *o2 = realloc(orient, sizeof(double) * 9 * (size_t) (n_max + 1));
+		if(r2 == NULL || o2 == NULL) die(&out, "out of memory\n");
+		r = r2;
+		orient = o2;
+	}
 
 	if(prm.ensemble == PP_NPT) {
 		pph_get_double(in, "rescale_factor_max", &prm.rescale_factor_max, 1);
@@ -273,6 +311,13 @@ int main(int argc, char *argv[]) {
 	pp_group *h = NULL;
 	if(pp_group_create(&prm, n_gpus, devices, &h) != 0) die(&out, "%s\n", h ? pp_group_last_error(h) : "pp_group_create failed");
 	if(n_gpus > 1) log_msg(&out, "Running on %d x-slabs\n", n_gpus);
+	pp_handle *engine0 = NULL;
+	if(ensemble == PP_HOST_GC || ensemble == PP_HOST_SUS) {
+		if(n_gpus != 1) die(&out, "Ensemble %d runs on a single engine (GPUs = 1)\n", ensemble);
+		if(prm.Lx_move) die(&out, "Lx_move is not available with Ensemble %d on the GPU path\n", ensemble);
+		PP_CALL(&out, h, pp_group_engine(h, 0, &engine0));
+		PP_CALL(&out, h, pp_reserve(engine0, n_max)); /* System.particles holds N_max of them (system.c:199) */
+	}
 	PP_CALL(&out, h, pp_group_upload(h, N, box, r, orient));
 	{
 		pp_observables o;
@@ -300,8 +345,13 @@ int main(int argc, char *argv[]) {
 	/* ---- main loop (main.c:78-120) -------------------------------------------------------------- */
 	llint step = out.start_from;
 	while(step < steps && !stop_requested) {
+		if(engine0 != NULL) { /* the particle number moves */
+			pp_observables o;
+			PP_CALL(&out, h, pp_group_get_observables(h, &o, 0));
+			N = o.N;
+		}
 		if(step % out.print_every == 0) {
-			print_observables(&out, h, &prm, step);
+			print_observables(&out, h, &prm, ensemble, step);
 			if(out.print_bonds) print_bonds(&out, h, N, step);
 			save_configuration(&out, h, N, step, out.conf_last, r, orient);
 			if(step != 0) { /* MC_check_energy + cells_check (main.c:85-87) */
@@ -310,6 +360,16 @@ int main(int argc, char *argv[]) {
 				PP_CALL(&out, h, pp_group_check_energy(h, &scratch, &ov, &ok));
 				if(ov) die(&out, "\nComputing energy from scratch resulted in an overlap, aborting\n");
 				if(!ok) die(&out, "\nEnergy check failed: %s\n", pp_group_last_error(h));
+				if(sus_hist != NULL) { /* output_and_reset_sus (output.c:343-356) */
+					snprintf(name, sizeof(name), "%s/sus-%lld.dat", sus_folder, step);
+					FILE *f = fopen(name, "w");
+					if(f == NULL) die(&out, "SUS file '%s' is not writable\n", name);
+					for(int i = 0; i < n_max - n_min + 1; i++) {
+						if(sus_hist[i] > 0) fprintf(f, "%d %lld\n", i + n_min, sus_hist[i]);
+						sus_hist[i] = 0;
+					}
+					fclose(f);
+				}
 			}
 		}
 		if(step > 0 && step % out.save_every == 0) {
@@ -324,21 +384,36 @@ int main(int argc, char *argv[]) {
 		if(ns < next) next = ns;
 		llint chunk = next - step;
 		if(chunk > 64) chunk = 64;
-		PP_CALL(&out, h, pp_group_sweep(h, chunk));
+		if(engine0 != NULL) { /* do_GC / do_SUS (MC.c:31-58): the step's insertion / removal trials, then its particle moves */
+			for(llint k = 0; k < chunk; k++) {
+				int full = 0;
+				PP_CALL(&out, h, pp_gc_step(engine0, activity, n_min, n_max, (long long *) sus_hist, NULL, &full));
+				if(full && ensemble == PP_HOST_GC)
+					die(&out, "The system contains the maximum number of particles set in the input file (%d), increase GC_N_max\n", n_max);
+				PP_CALL(&out, h, pp_group_sweep(h, 1));
+			}
+		}
+		else PP_CALL(&out, h, pp_group_sweep(h, chunk));
 		PP_CALL(&out, h, pp_group_sync(h));
 		step += chunk;
 	}
 
 	/* ---- last configuration and last line (main.c:125-132) ------------------------------------ */
+	if(engine0 != NULL) {
+		pp_observables o;
+		PP_CALL(&out, h, pp_group_get_observables(h, &o, 0));
+		N = o.N;
+	}
 	save_configuration(&out, h, N, step, out.conf_last, r, orient);
 	{
 		pp_observables o;
 		PP_CALL(&out, h, pp_group_get_observables(h, &o, 0));
 		printf("%lld %lf %lf", step, (o.N > 0) ? o.energy / o.N : 0., o.energy);
-		if(prm.ensemble != PP_NVT) printf(" %lf", o.N / o.volume);
+		if(ensemble != PP_NVT) printf(" %lf", o.N / o.volume);
 		printf("\n");
 	}
 
+	free(sus_hist);
 	pp_group_destroy(h);
 	free(r);
 	free(orient);

@@ -28,11 +28,13 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 2
+#define PP_ABI_VERSION 3
 
 /* move-type slots of System.tries[] / accepted[] (defs.h:11-19) */
 #define PP_N_MOVES 8
 #define PP_ROTO_TRASL 0
+#define PP_ADD 2
+#define PP_REMOVE 3
 #define PP_VOLUME 6
 #define PP_LX 7
 
@@ -136,6 +138,31 @@ int pp_check_energy(pp_handle *h, long long *bonds_scratch, int *overlap, int *o
  * dE[k] = reference deltaE (E_new = 0 when the new position overlaps), overlap[k], accept[k]. */
 int pp_eval_proposals(pp_handle *h, int n, const int *idx, const double *disp, const double *orient_new,
 		const double *u, int commit, int *dE, int *overlap, int *accept);
+
+/* ---- grand-canonical insertion / removal: MC_add_remove, MC.c:342-448, as do_GC / do_SUS call it
+ * (MC.c:31-58).  The engine is created with Ensemble = 0; the host alternates pp_gc_step and pp_sweep.  Single engine only. */
+typedef struct pp_gc_result {
+	int kind;        /* PP_ADD, PP_REMOVE, or -1: returned before a try (full system on insertion, N == n_min on removal) */
+	int accepted;
+	int overlap;     /* System.overlap as MC_energy left it */
+	int bonds;       /* -MC_energy of the inserted / removed particle (0 with an overlap, MC.c:296-299) */
+	int index;       /* index of the new particle (N) or of the one picked for removal */
+	int n_uniforms;  /* uniforms consumed */
+	int N;           /* particles after the move */
+} pp_gc_result;
+/* make room for up to n_max particles (GC_N_max / Umbrella_sampling_max, system.c:94-99, 199); call before pp_upload */
+int pp_reserve(pp_handle *h, int n_max);
+/* -MC_energy(syst, particles + id) (MC.c:272-309): bonded neighbours of one particle and the overlap flag, on the GPU */
+int pp_particle_bonds(pp_handle *h, int id, int *bonds, int *overlap);
+/* the same for a particle that is not there yet (MC.c:350-361): position r[3], orientation matrix orient[9] */
+int pp_probe_bonds(pp_handle *h, const double *r, const double *orient, int *bonds, int *overlap);
+/* Test hook: one MC_add_remove with the uniforms the reference would draw, in its order (MC.c:344, 352-354 + random_orientation,
+ * 364 / 383, 387) */
+int pp_add_remove(pp_handle *h, double activity, int n_min, int n_max, const double *u, int n_u, pp_gc_result *res);
+/* the insertion / removal trials of one MC step: Binomial(n_max, 0.01) of them (MC.c:33-36, 48-52) from the engine's own stream.
+ * sus_hist (may be NULL): SUS_hist[N - n_min]++ after every trial (MC.c:51); *full = 1 if an insertion met N == n_max (fatal
+ * under GC, MC.c:346). */
+int pp_gc_step(pp_handle *h, double activity, int n_min, int n_max, long long *sus_hist, int *n_trials, int *full);
 
 /* Test hooks: one MC_change_volume (MC.c:450-513) / MC_change_Lx (MC.c:515-585) with the uniforms
  * the reference would draw, in its draw order.  *accepted: 1 yes, 0 no, -1 early reject (Lx only). */

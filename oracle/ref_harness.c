@@ -232,6 +232,8 @@ void ref_run_steps(long n) {
 
 void ref_check_energy(void) { MC_check_energy(&g_syst, &g_out); }
 void ref_volume_move(void) { MC_change_volume(&g_syst, &g_out); }
+/* one MC_add_remove (MC.c:342-448) of a system opened with Ensemble = 1 (GC_N_max particles allocated, system.c:94, 199) */
+void ref_add_remove(void) { MC_add_remove(&g_syst, &g_out); }
 void ref_Lx_move(void) { MC_change_Lx(&g_syst, &g_out); }
 
 /* the reference's own helpers, driven directly (utils.c:115-131 draws from the drand48 above; utils.c:91-113) */

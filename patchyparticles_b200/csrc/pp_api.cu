@@ -539,7 +539,9 @@ static int upload_finish(pp_handle *h, int n, bool check_held, bool keep_books) 
 int upload_impl(pp_handle *h, int N_global, int n, const int *ids, const double *box, const double *r, const double *orient, bool keep_books) {
 	if(n < 0 || N_global < n) return fail(h, "bad particle numbers (%d local of %d)", n, N_global);
 	if(upload_begin(h, N_global, box, keep_books)) return 1;
-	size_t cap = (size_t) n, n_records = 0;
+	size_t cap = (size_t) n, n_records = 0, n_ids = (size_t) N_global;
+	if(h->slab_world <= 1 && (size_t) h->reserve_N > cap) cap = n_ids = (size_t) h->reserve_N; // room for insertions (pp_reserve)
+	if(cap < 4) cap = 4;
 	if(h->slab_world > 1) {
 		const int nx = h->n_side[0];
 		int *layer_count = (int *) calloc((size_t) nx, sizeof(int));
@@ -551,7 +553,7 @@ int upload_impl(pp_handle *h, int N_global, int n, const int *ids, const double 
 		free(layer_count);
 		slab_sizes(n, fullest, &cap, &n_records);
 	}
-	if(ensure_state(h, cap, (size_t) N_global, n_records)) return 1;
+	if(ensure_state(h, cap, n_ids, n_records)) return 1;
 	peer_release(h); // a new configuration: the driver connects the neighbours again
 	if(n > 0) {
 		CUDA_OK(h, cudaMemcpyAsync(h->d_stage_r, r, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, h->stream));
@@ -846,6 +848,7 @@ int pp_destroy(pp_handle *h) {
 	cudaFree(h->d_counters);
 	cudaFree(h->cb.bins);
 	cudaFree(h->d_slab_counts);
+	cudaFree(h->d_gc_out);
 	cudaFreeHost(h->h_slab_ints);
 	cudaFree(h->d_push_done);
 	cudaFree(h->d_peer_status);

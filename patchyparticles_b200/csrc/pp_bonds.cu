@@ -94,7 +94,7 @@ __global__ void k_zero_bonds(Counters *counters) {
 // -- a few per cent of the pairs in range -- is appended to a pair queue in global memory (per-block queue in shared
 // memory, one global atomic per block).
 // k_bonds_exact: one thread per queued pair, the reference's FP64 arithmetic (MC.c:233-262), integer reduction.
-// No FP64 code, no orientation matrix and no FP64 position is touched by the screen: it runs at 40 registers.
+// The screen runs no FP64 arithmetic and touches no FP64 position: 48 registers, ten blocks per SM.
 // The global overlap flag is polled by every block of both kernels: after the first overlap the rest returns at once,
 // like the reference's `while(!overlap_found)` loops (MC.c:488-495, 556-560).
 // Needs at least four cells per axis (the half shell would meet a cell twice on an axis with two); smaller grids
@@ -107,7 +107,7 @@ __global__ void k_zero_bonds(Counters *counters) {
 constexpr int kPencilMaxThreads = 128;
 constexpr int kPencilMaxCells = 96;   // cells of a pencil per block
 constexpr int kPencilMaxCap = 288;    // staged shadows per column (hard spheres: < 2 per cell of side r_cut)
-constexpr int kPencilQueue = 512;     // queued pairs per block
+constexpr int kPencilQueue = 192;     // queued pairs per block (beyond: straight to the global queue)
 
 // per column of the half shell: where its staged run comes from -- [copy of cell nz - 1][cells z_lo .. z_hi - 1][copy of cell 0]
 struct PencilColumn {
@@ -120,7 +120,7 @@ __device__ __forceinline__ int pencil_slot(const PencilColumn &pc, int j) { // s
 	return j < pc.n_lw ? pc.lw0 + j : (j < pc.n_lw + pc.n_main ? pc.g0 + (j - pc.n_lw) : pc.hw0 + (j - pc.n_lw - pc.n_main));
 }
 
-__global__ void __launch_bounds__(kPencilMaxThreads, 8) k_bonds_screen(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
+__global__ void __launch_bounds__(kPencilMaxThreads, 10) k_bonds_screen(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
 		const int *__restrict__ cell_sorted, const double *__restrict__ ori, const uint4 *__restrict__ posf, const Counters *counters, int2 *queue,
 		const int queue_cap, const int seg_cells, const int n_seg, const int cap) {
 	constexpr int kRow = kPencilMaxCells + 3;
@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(kPencilMaxThreads, 8) k_bonds_screen(const __g
 	int *s_beg = reinterpret_cast<int *>(s_q + kPencilQueue);                       // [5][kRow]: staged index of the first member of window cell k (k = nk: the end)
 	if(tid == 0) s_nq = 0;
 
-	// ---- cell bounds of the five columns ------------------------------------------------------------------------
-	for(int i = tid; i < 5 * (nk + 1); i += blockDim.x) {
+	// ---- cell bounds of the five columns: one round trip (the loads of an iteration are independent, iterations unrolled) ----
+	const int n_items = 5 * (nk + 1);
+#pragma unroll 4
+	for(int i = tid; i < n_items; i += blockDim.x) {
 		const int c = i / (nk + 1), k = i - c * (nk + 1);
 		const int dx = c >= 2, dy = c == 0 ? 0 : (c == 1 ? 1 : c - 3);
 		int cx = ix + dx;
@@ -150,34 +152,53 @@ __global__ void __launch_bounds__(kPencilMaxThreads, 8) k_bonds_screen(const __g
 		cy += (cy < 0) ? ny : 0;
 		cy -= (cy >= ny) ? ny : 0;
 		const int *cs = cell_start + (cx * ny + cy) * nz;
-		PencilColumn pc;
-		pc.g0 = cs[z_lo];
-		pc.n_main = cs[z_hi] - pc.g0;
-		pc.lw0 = cs[nz - 1];
-		pc.n_lw = z0 == 0 ? cs[nz] - pc.lw0 : 0;
-		pc.hw0 = cs[0];
-		pc.n_hw = z1 == nz ? cs[1] - pc.hw0 : 0;
-		const int z = z0 - 1 + k; // k = nk: one past the last window cell
+		const int z = z0 - 1 + k; // -1 .. nz + 1; k = nk is one past the last window cell
+		// the run is staged as [copy of cell nz - 1 (z0 == 0)][cells z_lo .. z_hi - 1][copy of cell 0 (z1 == nz)]
+		const int g0 = cs[z_lo], c_first = cs[0], c_second = cs[1], c_last = cs[nz - 1], c_end = cs[nz], c_z = cs[min(max(z, 0), nz)];
+		const int n_lw = z0 == 0 ? c_end - c_last : 0, n_hw = z1 == nz ? c_second - c_first : 0;
 		int at;
 		if(z < 0) at = 0;
-		else if(z < z_hi) at = pc.n_lw + (cs[z] - pc.g0);
-		else if(z == z_hi) at = pc.n_lw + pc.n_main;
-		else at = pc.n_lw + pc.n_main + pc.n_hw;
+		else if(z <= nz) at = n_lw + (c_z - g0);
+		else at = n_lw + (c_end - g0) + n_hw;
 		s_beg[c * kRow + k] = at;
-		if(k == 0) s_col[c] = pc;
+		if(k == 0) {
+			PencilColumn pc;
+			pc.g0 = g0;
+			pc.n_main = cs[z_hi] - g0;
+			pc.lw0 = c_last;
+			pc.n_lw = n_lw;
+			pc.hw0 = c_first;
+			pc.n_hw = n_hw;
+			s_col[c] = pc;
+		}
 	}
 	__syncthreads();
+	int tot[5];
 	bool fits = true;
 #pragma unroll
-	for(int c = 0; c < 5; c++) fits &= s_col[c].n_main + s_col[c].n_lw + s_col[c].n_hw <= cap;
+	for(int c = 0; c < 5; c++) {
+		tot[c] = s_col[c].n_main + s_col[c].n_lw + s_col[c].n_hw;
+		fits &= tot[c] <= cap;
+	}
+	const PencilColumn own = s_col[0];
+	const int own_first = pencil_slot(own, s_beg[1]), n_own = s_beg[nk - 1] - s_beg[1];
+	// this thread's particle (first round): its cell and matrix are on their way while the shadows are staged
+	int cell_p = 0;
+	double m_p[9];
+	if(tid < n_own) {
+		cell_p = cell_sorted[own_first + tid];
+#pragma unroll
+		for(int k = 0; k < 9; k++) m_p[k] = ori[9ll * (own_first + tid) + k];
+	}
 
-	// ---- the five runs of shadows ---------------------------------------------------------------------------------
+	// ---- the five runs of shadows, as one flat copy ---------------------------------------------------------------
 	if(fits) {
-#pragma unroll 1
-		for(int c = 0; c < 5; c++) {
-			const PencilColumn pc = s_col[c];
-			const int total = pc.n_main + pc.n_lw + pc.n_hw;
-			for(int i = tid; i < total; i += blockDim.x) s_stage[c * cap + i] = posf[pencil_slot(pc, i)];
+		const int t1 = tot[0], t2 = t1 + tot[1], t3 = t2 + tot[2], t4 = t3 + tot[3], t5 = t4 + tot[4];
+#pragma unroll 4
+		for(int i = tid; i < t5; i += blockDim.x) {
+			const int c = (i >= t1) + (i >= t2) + (i >= t3) + (i >= t4);
+			const int j = i - (c == 0 ? 0 : (c == 1 ? t1 : (c == 2 ? t2 : (c == 3 ? t3 : t4))));
+			s_stage[c * cap + j] = posf[pencil_slot(s_col[c], j)];
 		}
 	}
 	__syncthreads();
@@ -185,17 +206,20 @@ __global__ void __launch_bounds__(kPencilMaxThreads, 8) k_bonds_screen(const __g
 	const float ux = (float) (sc.box[0] / 4294967296.), uy = (float) (sc.box[1] / 4294967296.), uz = (float) (sc.box[2] / 4294967296.);
 	const float thr = (float) sc.sqr_rcut + 2e-3f, core_hi = 1.f + 2e-3f;
 	const float point_thr = sc.fast_patch ? (float) (sc.cos2_lo * sc.inv_b2) * (1.f - 2e-3f) : -1.f;
-	const PencilColumn own = s_col[0];
-	const int *cs_own = cell_start + (ix * ny + iy) * nz;
-	const int own_first = cs_own[z0], n_own = cs_own[z1] - own_first;
 	for(int base = 0; base < n_own; base += blockDim.x) {
 		const int sp = own_first + base + tid;
 		if(base + tid < n_own) {
-			const int k_own = cell_sorted[sp] % nz - z0 + 1;
+			if(base > 0) { // (more particles than threads: a dense packing)
+				cell_p = cell_sorted[sp];
+#pragma unroll
+				for(int k = 0; k < 9; k++) m_p[k] = ori[9ll * sp + k];
+			}
+			float mf[9];
+#pragma unroll
+			for(int k = 0; k < 9; k++) mf[k] = (float) m_p[k];
+			const int k_own = cell_p % nz - z0 + 1;
 			const int j_own = own.n_lw + (sp - own.g0); // staged index of the particle itself (column 0)
 			const uint4 sh = fits ? s_stage[j_own] : posf[sp];
-			float mf[9];
-			bool have_m = false;
 			// the five ranges as one loop: column 0 from the particle itself to the end of the cell above, the others three cells
 			int c = 0, j = j_own + 1, e = s_beg[k_own + 2];
 			while(true) {
@@ -210,14 +234,7 @@ __global__ void __launch_bounds__(kPencilMaxThreads, 8) k_bonds_screen(const __g
 				const float ax = shadow_sep(qh.x, sh.x, ux), ay = shadow_sep(qh.y, sh.y, uy), az = shadow_sep(qh.z, sh.z, uz);
 				const float d2 = fmaf(az, az, fmaf(ay, ay, ax * ax));
 				if(d2 >= thr) continue;
-				if(d2 >= core_hi && point_thr >= 0.f) {
-					if(!have_m) {
-#pragma unroll
-						for(int k = 0; k < 9; k++) mf[k] = (float) ori[9ll * sp + k];
-						have_m = true;
-					}
-					if(!may_point(mf, ax, ay, az, d2, point_thr)) continue;
-				}
+				if(d2 >= core_hi && !may_point(mf, ax, ay, az, d2, point_thr)) continue;
 				const int2 pair = make_int2(sp, (int) qh.w); // the shadow carries its slot
 				const int slot = atomicAdd(&s_nq, 1);
 				if(slot < kPencilQueue) s_q[slot] = pair;
@@ -257,17 +274,19 @@ __global__ void __launch_bounds__(128) k_bonds_exact(const __grid_constant__ Sim
 	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		if(*((volatile int *) &counters->overlap) != 0) break;
 		const int2 pr = queue[1 + i];
-		const double4 p4 = pos[pr.x];
+		// both positions and both matrices in one round trip (most queued pairs are inside the shell and need them all)
+		const double4 p4 = pos[pr.x], q4 = pos[pr.y];
+		double m[9], mq[9];
+#pragma unroll
+		for(int k = 0; k < 9; k++) {
+			m[k] = ori[9ll * pr.x + k];
+			mq[k] = ori[9ll * pr.y + k];
+		}
 		const Vec3 p = {p4.x, p4.y, p4.z};
 		Vec3 d;
-		const double d2 = min_image(sc, p, pos[pr.y], d);
+		const double d2 = min_image(sc, p, q4, d);
 		if(d2 < 1.) overlap = 1;
-		else if(d2 < sc.sqr_rcut) {
-			double m[9];
-#pragma unroll
-			for(int k = 0; k < 9; k++) m[k] = ori[9ll * pr.x + k];
-			bonds += patches_bond_m(sc, d, d2, m, ori + 9ll * pr.y) ? 1 : 0;
-		}
+		else if(d2 < sc.sqr_rcut) bonds += patches_bond_m(sc, d, d2, m, mq) ? 1 : 0;
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
@@ -310,7 +329,9 @@ int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cel
 		int cap = (int) ((seg_cells + 4) * (occ > 1. ? 2. * occ : 2.)) + 16;
 		if(cap > kPencilMaxCap) cap = kPencilMaxCap;
 		const double own = occ * seg_cells; // particles of a block
-		const int threads = own <= 24. ? 32 : (own <= 56. ? 64 : kPencilMaxThreads);
+		// a grid that fits the machine at once is latency bound: the widest block brings the bounds and the shadows in the fewest rounds
+		const bool small = n_pencils * n_seg <= 148 * 10;
+		const int threads = small ? kPencilMaxThreads : (own <= 26. ? 32 : (own <= 56. ? 64 : (own <= 84. ? 96 : kPencilMaxThreads)));
 		const size_t smem = sizeof(uint4) * 5 * cap + sizeof(int2) * kPencilQueue + sizeof(int) * 5 * (kPencilMaxCells + 3);
 		k_bonds_screen<<<(unsigned) (n_pencils * n_seg), threads, smem, st>>>(sc, cell_start, cell_sorted, ori, posf, counters, queue, queue_cap, seg_cells,
 				n_seg, cap);

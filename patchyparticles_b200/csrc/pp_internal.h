@@ -51,6 +51,8 @@ struct pp_handle {
 	// staging for upload / download / proposals
 	double *d_stage_r, *d_stage_o;
 	pp::Proposal *d_proposals; // one per trial of a sweep
+	int reserve_N;             // pp_reserve: the arrays are sized for this many particles (insertions, pp_gc.cu)
+	int *d_gc_out;             // bonds and overlap flag of a single-particle probe
 
 	// grid
 	int n_side[3];

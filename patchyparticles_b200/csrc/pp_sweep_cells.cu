@@ -336,6 +336,7 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 
 			// ---- 4. Metropolis (MC.c:332-339) ------------------------------------------------
 			const int dE = b_old - b_new; // energy = -bonds
+			if(kOwn) __syncwarp(gmask); // every lane has read the particle's staged state (the shuffles above order execution, not memory)
 			if(is_owner) {
 				if(dE < 0 || pr->u_acc < sc.exp_table[dE < kMaxExp ? dE : kMaxExp - 1]) {
 					double *p = reinterpret_cast<double *>(pos + sp); // x, y, z; the id in .w stays

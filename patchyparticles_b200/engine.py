@@ -60,7 +60,13 @@ ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy",
                "pp_slab_box_trial", "pp_slab_box_finish", "pp_group_create", "pp_group_destroy", "pp_group_last_error",
                "pp_group_upload", "pp_group_download", "pp_group_total_bonds", "pp_group_bond_lists", "pp_group_sweep",
                "pp_group_sync", "pp_group_get_observables", "pp_group_check_energy", "pp_group_volume_move",
-               "pp_group_Lx_move", "pp_group_engine"]
+               "pp_group_Lx_move", "pp_group_engine", "pp_reserve", "pp_particle_bonds", "pp_probe_bonds", "pp_add_remove", "pp_gc_step"]
+
+
+class GCResult(C.Structure):
+    """pp_gc_result (include/pp_b200.h)"""
+    _fields_ = [("kind", C.c_int), ("accepted", C.c_int), ("overlap", C.c_int), ("bonds", C.c_int), ("index", C.c_int),
+                ("n_uniforms", C.c_int), ("N", C.c_int)]
 
 
 class PeerInfo(C.Structure):
@@ -141,6 +147,11 @@ def load_library():
     L.pp_slab_sweeps.argtypes = [H, C.c_int, PI]
     L.pp_slab_migrate.argtypes = [H, PI]
     L.pp_slab_download.argtypes = [H, PI, _ip, _dp, _dp]
+    L.pp_reserve.argtypes = [H, C.c_int]
+    L.pp_particle_bonds.argtypes = [H, C.c_int, PI, PI]
+    L.pp_probe_bonds.argtypes = [H, _dp, _dp, PI, PI]
+    L.pp_add_remove.argtypes = [H, C.c_double, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(GCResult)]
+    L.pp_gc_step.argtypes = [H, C.c_double, C.c_int, C.c_int, C.c_void_p, PI, PI]
     _lib = L
     return L
 
@@ -267,6 +278,40 @@ class Engine:
         a = C.c_int(0)
         self._check(self.L.pp_Lx_move(self.h, u_lx, u_acc, C.byref(a)))
         return int(a.value)
+
+    # ---- grand-canonical insertion / removal (MC_add_remove, MC.c:342-448) ------------------------
+    def reserve(self, n_max):
+        """room for up to n_max particles; before upload"""
+        self._check(self.L.pp_reserve(self.h, int(n_max)))
+
+    def particle_bonds(self, idx):
+        b, ov = C.c_int(0), C.c_int(0)
+        self._check(self.L.pp_particle_bonds(self.h, int(idx), C.byref(b), C.byref(ov)))
+        return int(b.value), int(ov.value)
+
+    def probe_bonds(self, r, orient):
+        b, ov = C.c_int(0), C.c_int(0)
+        self._check(self.L.pp_probe_bonds(self.h, np.ascontiguousarray(r, dtype=np.float64).reshape(3),
+                                          np.ascontiguousarray(orient, dtype=np.float64).reshape(9), C.byref(b), C.byref(ov)))
+        return int(b.value), int(ov.value)
+
+    def add_remove(self, activity, n_min, n_max, uniforms):
+        """one MC_add_remove with recorded uniforms -> GCResult"""
+        u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1)
+        res = GCResult()
+        self._check(self.L.pp_add_remove(self.h, float(activity), int(n_min), int(n_max), u, int(u.size), C.byref(res)))
+        self.N = int(res.N)
+        return res
+
+    def gc_step(self, activity, n_min, n_max, hist=None):
+        """the insertion / removal trials of one MC step -> (trials, full); hist: int64 array of n_max - n_min + 1 bins (SUS)"""
+        n, full = C.c_int(0), C.c_int(0)
+        hp = hist.ctypes.data_as(C.c_void_p) if hist is not None else None
+        self._check(self.L.pp_gc_step(self.h, float(activity), int(n_min), int(n_max), hp, C.byref(n), C.byref(full)))
+        o = Observables()
+        self._check(self.L.pp_get_observables(self.h, C.byref(o), 0))
+        self.N = int(o.N)
+        return int(n.value), int(full.value)
 
     # ---- x-slab decomposition hooks (see slab.py) ------------------------------------------------
     def slab_setup(self, rank, world):

@@ -406,6 +406,20 @@ class RefSystem:
         self.set_stream(None)
         return int(self.counters()[1][slot]) - before, used, self.box(), self.running_energy(), self.cells()
 
+    def add_remove(self, uniforms):
+        """One MC_add_remove (MC.c:342-448) fed with the given uniforms in the reference's draw order ->
+        (kind: 2 insertion, 3 removal, -1 returned before a try; accepted; uniforms consumed; N; running energy)."""
+        t0, a0 = self.counters()
+        self.set_stream(uniforms)
+        self.L.ref_add_remove()
+        used = int(self.L.ref_stream_pos())
+        self.set_stream(None)
+        t1, a1 = self.counters()
+        kind = 2 if t1[2] > t0[2] else (3 if t1[3] > t0[3] else -1)
+        accepted = int(a1[2] - a0[2] + a1[3] - a0[3])
+        self.N = self.L.ref_N()
+        return kind, accepted, used, self.N, self.running_energy()
+
     def random_vector_on_sphere(self, uniforms):
         """utils.c:115-131 fed with the given uniforms -> (axis, uniforms consumed)"""
         out = np.zeros(3)

@@ -449,3 +449,33 @@ def test_box_move_into_too_small_box_is_rejected(pp):
     e.sweep(20)  # NPT steps with more such trials in them
     assert e.check_energy()[2]
     e.close()
+
+
+def test_gc_moves_golden(pp):
+    """MC_add_remove (MC.c:342-448): the engine, fed the recorded uniforms of tests/golden/gc_moves.npz, takes the decisions the
+    reference's own MC_add_remove took (400 moves, insertions and removals, 49 accepted), consumes the same number of uniforms,
+    follows the same N and running energy, and ends in the same configuration -- index for index (a new particle is N, the
+    last particle takes the index of a removed one), positions and orientation matrices bit for bit."""
+    g = load_golden("gc_moves")
+    delta, cosmax, T, z, n_min, n_max = g["params"]
+    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T, seed=1)
+    e.reserve(int(n_max))
+    e.upload(g["box"], g["r"], g["orient"])
+    bonds, ov = e.total_bonds()
+    assert ov == 0 and -bonds == g["energy0"][0]
+    # single-particle energies against the reference's per-particle counts (MC_energy, MC.c:272-309)
+    counts = e.bond_counts()
+    for i in (0, 17, 512, 999):
+        assert e.particle_bonds(i) == (counts[i], 0)
+    for k in range(len(g["u"])):
+        res = e.add_remove(z, int(n_min), int(n_max), g["u"][k])
+        assert (res.kind, res.accepted, res.n_uniforms, res.N) == (g["kind"][k], g["accepted"][k], g["used"][k], g["N"][k]), f"move {k}"
+        assert e.observables().energy == g["energies"][k], f"move {k}"
+    r, m = e.download()
+    assert np.array_equal(r, g["r_final"]) and np.array_equal(m, g["orient_final"])
+    b2, ov2, ok = e.check_energy()
+    assert ok and ov2 == 0 and -b2 == g["energies"][-1]
+    e.sweep(3)  # the sweep runs on the edited particle set
+    b3, ov3, ok3 = e.check_energy()
+    assert ok3 and ov3 == 0
+    e.close()

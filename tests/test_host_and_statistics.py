@@ -251,3 +251,55 @@ def test_lx_statistics_vs_reference(tmp_path):
         print(f"{name}: ref {m_ref:.4f} +- {s_ref:.4f}   gpu {m_gpu:.4f} +- {s_gpu:.4f}")
         assert lo < m_ref < hi
         assert abs(m_gpu - m_ref) < 3.0 * np.hypot(s_ref, s_gpu), name
+
+
+def test_gc_statistics_vs_reference(tmp_path):
+    """Ensemble = 1 (do_GC, MC.c:31-44; MC_add_remove, MC.c:342-448): <N>, the spread of N, <E>/N and the insertion / removal
+    acceptances of the C host (insertion energies probed on the GPU) against the reference binary on the same input file.
+    A dilute bonded gas (activity 0.05 in a box of side 10): N decorrelates within tens of steps."""
+    need_binaries()
+    keys = dict(Ensemble=1, Temperature=0.3, Activity=0.05, GC_N_max=200, Print_every=20)
+    d_ref, d_gpu = make_case(tmp_path, 50, 0.05, Steps=30000, **keys)
+    run(REF_BIN, d_ref)
+    run(HOST_BIN, d_gpu)
+    discard = 2000
+    res = {}
+    for tag, d in (("ref", d_ref), ("gpu", d_gpu)):
+        rho = load_cols(d / "density.dat")
+        a = load_cols(d / "acceptance.dat")
+        e = load_cols(d / "energy.dat")
+        assert rho.shape[1] == 3 and a.shape[1] == 4  # step rho N; step roto add remove (output.c:166-170)
+        n = rho[rho[:, 0] >= discard, 2]
+        a = a[a[:, 0] >= discard]
+        res[tag] = (block_stats(n), block_stats((n - n.mean()) ** 2), block_stats(a[np.isfinite(a[:, 2]), 2]), block_stats(a[np.isfinite(a[:, 3]), 3]),
+                    block_stats(e[e[:, 0] >= discard, 1]))
+        import patchyparticles_b200 as pkg
+        step, box, r, m = pkg.read_rrr(str(d / "last.rrr"))
+        assert step == 30000 and abs(len(r) - rho[-1, 2]) < 25  # last.rrr holds the particles the run ended with (20 steps after the last print)
+    for name, k, lo, hi in (("<N>", 0, 30., 70.), ("var N", 1, 10., 120.), ("insertion acceptance", 2, 0.3, 1.0), ("removal acceptance", 3, 0.3, 1.0),
+                            ("E/N", 4, -0.5, 0.0)):
+        (m_ref, s_ref), (m_gpu, s_gpu) = res["ref"][k], res["gpu"][k]
+        print(f"{name}: ref {m_ref:.4f} +- {s_ref:.4f}   gpu {m_gpu:.4f} +- {s_gpu:.4f}")
+        assert lo < m_ref < hi, name
+        assert abs(m_gpu - m_ref) < 3.0 * np.hypot(s_ref, s_gpu), name
+
+
+def test_sus_histogram_files(tmp_path):
+    """Ensemble = 3 (do_SUS, MC.c:46-58): N stays inside the umbrella window and every print point after the first leaves a
+    sus-<step>.dat with the visits since the previous one (output.c:343-356)."""
+    need_binaries()
+    (tmp_path / "gpu").mkdir()
+    d = tmp_path / "gpu"
+    subprocess.run([GEN_BIN, "50", "0.05"], cwd=tmp_path, check=True, stderr=subprocess.DEVNULL)
+    (d / "sus").mkdir()
+    write_input(d / "input", Dynamics=0, Ensemble=3, Temperature=0.3, Steps=3000, Disp_max=0.2, Theta_max=0.3,
+                Initial_conditions_file=str(tmp_path / "generated.rrr"), Print_every=1000, Save_every=100000000, Configuration_folder=".",
+                KF_delta=0.119, KF_cosmax=0.92, Seed=5, Log_file="none", Activity=0.05, Umbrella_sampling_min=44, Umbrella_sampling_max=56,
+                Umbrella_sampling_folder="sus")
+    run(HOST_BIN, d)
+    rho = load_cols(d / "density.dat")
+    assert np.all(rho[:, 2] >= 44) and np.all(rho[:, 2] <= 56)
+    for step in (1000, 2000):
+        h = load_cols(d / "sus" / f"sus-{step}.dat")
+        assert np.all(h[:, 0] >= 44) and np.all(h[:, 0] <= 56) and np.all(h[:, 1] > 0)
+        assert 400 < h[:, 1].sum() < 720  # Binomial(56, 0.01) trials per step: about 560 per thousand steps (MC.c:48-52)

@@ -336,7 +336,7 @@ def test_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(pkg.library_path())
     for name in sorted(declared):
         assert hasattr(lib, name), name
-    assert lib.pp_abi_version() == 2
+    assert lib.pp_abi_version() == 3
     assert ctypes.sizeof(pkg.Params) >= 120
 
 
@@ -362,3 +362,34 @@ def test_product_does_not_import_oracle():
                     if re.search(r'#include\s+"[^"]*oracle|import\s+_oracle|from\s+_oracle|libpporacle|libppref|ppo_[a-z_]+\s*\(', text):
                         bad.append(os.path.join(dirpath, fn))
     assert not bad, bad
+
+
+def test_gc_golden_fixture(oracle, tmp_path):
+    """tests/golden/gc_moves.npz (the reference's own MC_add_remove, MC.c:342-448, fed recorded uniforms): the file is
+    consistent with the move it records, and -- where the reference library is present -- the reference replayed live takes
+    the same decisions, so the fixture is what tools/make_golden.py gc_moves produces."""
+    g = load_golden("gc_moves")
+    kind, acc, used, Ns, en = g["kind"], g["accepted"], g["used"], g["N"], g["energies"]
+    assert set(np.unique(kind)) <= {2, 3} and (acc[kind == 2].sum(), acc[kind == 3].sum()) == (29, 20)
+    n_prev = len(g["r"])
+    for k in range(len(kind)):
+        assert Ns[k] == n_prev + (acc[k] if kind[k] == 2 else -acc[k])
+        assert (g["u"][k, 0] < 0.5) == (kind[k] == 2)          # MC.c:344
+        if kind[k] == 3:
+            assert used[k] == 3                                 # which move, which particle, acceptance (MC.c:344, 383, 387)
+        else:
+            assert used[k] >= 10 and (used[k] - 4) % 2 in (0, 1)  # 1 + 3 + three Marsaglia points (>= 2 each) [+ acceptance without an overlap]
+        n_prev = Ns[k]
+    assert np.all(en == np.round(en)) and len(g["r_final"]) == Ns[-1]
+    if not oracle.have_ref():
+        return
+    rrr = str(tmp_path / "warm.rrr")
+    oracle.write_rrr(rrr, 0, g["box"], g["r"], g["orient"].reshape(-1, 9))
+    delta, cosmax, T, z, n_min, n_max = g["params"]
+    ref = oracle.RefSystem(rrr, Ensemble=1, Activity=z, GC_N_max=int(n_max), KF_delta=delta, KF_cosmax=cosmax, Temperature=T)
+    e, ov = ref.total_energy()
+    assert (e, ov) == (g["energy0"][0], 0)
+    ref.set_running_energy(e)
+    for k in range(120):
+        assert ref.add_remove(g["u"][k]) == (kind[k], acc[k], used[k], Ns[k], en[k]), f"move {k}"
+    ref.close()

@@ -191,6 +191,45 @@ def box_moves():
     np.savez_compressed(os.path.join(GOLD, "box_moves.npz"), **out)
 
 
+def gc_moves():
+    """tests/golden/gc_moves.npz: the reference's own MC_add_remove (MC.c:342-448) driven one move at a time on the warm state
+    (opened with Ensemble = 1, Activity = 0.5, GC_N_max = N + 40), each move fed 64 recorded uniforms in the reference's draw
+    order (insert or remove; position; random_orientation; acceptance / index; acceptance).  Per move: kind (2 insertion,
+    3 removal), accepted, uniforms consumed, N and running energy afterwards; the final configuration in index order."""
+    g = np.load(os.path.join(GOLD, "warm1000.npz"))
+    tmp = "/tmp/_golden_warm.rrr"
+    O.write_rrr(tmp, 0, g["box"], g["r"], g["orient"].reshape(-1, 9))
+    N0 = len(g["r"])
+    z, n_max = 0.5, N0 + 40
+    ref = O.RefSystem(tmp, Ensemble=1, Activity=z, GC_N_max=n_max, **WARM)
+    r, m = ref.state()
+    e, ov = ref.total_energy()
+    assert ov == 0
+    ref.set_running_energy(e)
+    rng = np.random.default_rng(41)
+    n = 400
+    u = rng.random((n, 64))
+    u[1::2, 0] = 0.5 * u[1::2, 0]                # every other move is an insertion for certain ...
+    u[1::4, 1:4] = 0.02 + 0.04 * u[1::4, 1:4]    # ... and half of those land in one corner of the box (insertions next to earlier insertions)
+    u[0::4, 2] *= 1e-4                           # removals (when the first uniform says so) with an acceptance draw that a bonded particle passes
+    kind = np.zeros(n, dtype=np.int32)
+    acc = np.zeros(n, dtype=np.int32)
+    used = np.zeros(n, dtype=np.int32)
+    Ns = np.zeros(n, dtype=np.int32)
+    en = np.zeros(n)
+    for k in range(n):
+        kind[k], acc[k], used[k], Ns[k], en[k] = ref.add_remove(u[k])
+    r2, m2 = ref.state()
+    e2, ov2 = ref.total_energy()
+    assert ov2 == 0 and e2 == en[-1], (e2, en[-1])
+    ref.close()
+    print("gc moves: insertions", int(np.sum(kind == 2)), "accepted", int(np.sum(acc[kind == 2])), "removals", int(np.sum(kind == 3)), "accepted",
+          int(np.sum(acc[kind == 3])), "N", N0, "->", Ns[-1], "E", e, "->", e2, "uniforms used", np.bincount(used)[:20])
+    np.savez_compressed(os.path.join(GOLD, "gc_moves.npz"), r=r, orient=m, box=g["box"], energy0=np.array([e]),
+                        params=np.array([WARM["KF_delta"], WARM["KF_cosmax"], WARM["Temperature"], z, 0, n_max]), u=u, kind=kind, accepted=acc,
+                        used=used, N=Ns, energies=en, r_final=r2, orient_final=m2)
+
+
 def helpers():
     """tests/golden/helpers.npz: the reference's random_vector_on_sphere (utils.c:115-131) fed with recorded uniforms
     (axis + number of uniforms consumed) and its gram_schmidt (utils.c:91-113) on perturbed orientation matrices."""
@@ -223,6 +262,8 @@ def main():
         return warm()
     if len(sys.argv) > 1 and sys.argv[1] == "box_moves":
         return box_moves()
+    if len(sys.argv) > 1 and sys.argv[1] == "gc_moves":
+        return gc_moves()
     one("fcc", os.path.join(REF, "fcc.rrr"), {"a": {}, "b": {"KF_cosmax": 0.92}}, n_prop=2048, T=0.11)
     one("bcc", os.path.join(REF, "bcc.rrr"), {"a": {}, "b": {"KF_delta": 0.135}}, n_prop=1024)
     tmp = "/tmp/_golden_gen.rrr"
@@ -235,6 +276,7 @@ def main():
     bond_lists()
     warm()
     box_moves()
+    gc_moves()
     helpers()
     known = {}
     for N, rho in [(32768, 0.3), (65536, 0.5)]:
