@@ -164,6 +164,16 @@ int pp_add_remove(pp_handle *h, double activity, int n_min, int n_max, const dou
  * under GC, MC.c:346). */
 int pp_gc_step(pp_handle *h, double activity, int n_min, int n_max, long long *sus_hist, int *n_trials, int *full);
 
+/* ---- neighbour queries of the cluster moves; the moves themselves stay on the host.  A batch of n particles
+ * per call, answered from the cell-sorted state with the reference's pair arithmetic; single engine only. */
+/* _set_neighbours (avb.c:43-75): neighbours[k * 4 + patch] = index of the neighbour bonded through that patch of particle idx[k]
+ * (MC_interact's onp, MC.c:249-261; -1: free; where two neighbours share a patch the last one in the reference's cell order and
+ * ascending index inside a cell stays), num_neighbours[k] = number of bonded neighbours */
+int pp_patch_neighbours(pp_handle *h, int n, const int *idx, int *neighbours, int *num_neighbours);
+/* the geometric part of _populate_possible_links (vmmc.c:148-229): the particles within the interaction range of idx[k]
+ * (dist2 < kf_sqr_rcut, vmmc.c:178), first max_per_particle of them in the same order, -1 beyond counts[k] */
+int pp_range_neighbours(pp_handle *h, int n, const int *idx, int max_per_particle, int *counts, int *neighbours);
+
 /* Test hooks: one MC_change_volume (MC.c:450-513) / MC_change_Lx (MC.c:515-585) with the uniforms
  * the reference would draw, in its draw order.  *accepted: 1 yes, 0 no, -1 early reject (Lx only). */
 int pp_volume_move(pp_handle *h, double u_dir, double u_vol, double u_acc, int *accepted);

@@ -173,6 +173,27 @@ void ref_bond_lists(int max_nb, int *counts, int *neigh) {
 	}
 }
 
+/* what AVB's _set_neighbours (avb.c:43-75) collects, by the same MC_interact over ALL pairs in ascending index: per particle the
+ * bonded neighbours with the patch of p (onp) and of q (onq) the reference reports */
+void ref_patch_pairs(int max_nb, int *counts, int *q_idx, int *q_onp, int *q_onq) {
+	int i, j, onp, onq;
+	for(i = 0; i < g_syst.N; i++) {
+		int n = 0;
+		for(j = 0; j < g_syst.N; j++) {
+			if(j == i) continue;
+			if(MC_interact(&g_syst, g_syst.particles + i, g_syst.particles + j, &onp, &onq) == PATCH_BOND) {
+				if(n < max_nb) {
+					q_idx[(size_t) i * max_nb + n] = j;
+					q_onp[(size_t) i * max_nb + n] = onp;
+					q_onq[(size_t) i * max_nb + n] = onq;
+				}
+				n++;
+			}
+		}
+		counts[i] = n;
+	}
+}
+
 void ref_rotate(const double *orient_old, const double *axis, double theta, double *orient_new) {
 	matrix o, n;
 	vector a = {axis[0], axis[1], axis[2]};

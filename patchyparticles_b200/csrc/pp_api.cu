@@ -413,7 +413,11 @@ int count_bonds(pp_handle *h, int p, const double *box, const double *shift, lon
 	const SimConst sc = make_const(h, box, shift);
 	prof_begin(h);
 	// the proposals of a sweep are dead between sweeps: their buffer holds the pair queue of the streaming count
-	const size_t scratch_bytes = (size_t) h->cap_N * sizeof(Proposal);
+	size_t scratch_bytes = (size_t) h->cap_N * sizeof(Proposal);
+	if(const char *limit = getenv("PP_BONDS_QUEUE_BYTES")) { // test hook: a small queue exercises the overflow path below
+		const long long b = atoll(limit);
+		if(b >= 0 && (size_t) b < scratch_bytes) scratch_bytes = (size_t) b;
+	}
 	const int nl = launch_total_bonds(sc, h->cb.cell_start, h->cb.cell_sorted, h->pos[p], h->ori[h->co], h->cb.posf, h->d_counters, h->d_proposals,
 			scratch_bytes, false, h->stream);
 	prof_end(h, PP_K_BONDS, nl);

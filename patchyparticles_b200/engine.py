@@ -60,7 +60,8 @@ ABI_SYMBOLS = ["pp_default_params", "pp_abi_version", "pp_create", "pp_destroy",
                "pp_slab_box_trial", "pp_slab_box_finish", "pp_group_create", "pp_group_destroy", "pp_group_last_error",
                "pp_group_upload", "pp_group_download", "pp_group_total_bonds", "pp_group_bond_lists", "pp_group_sweep",
                "pp_group_sync", "pp_group_get_observables", "pp_group_check_energy", "pp_group_volume_move",
-               "pp_group_Lx_move", "pp_group_engine", "pp_reserve", "pp_particle_bonds", "pp_probe_bonds", "pp_add_remove", "pp_gc_step"]
+               "pp_group_Lx_move", "pp_group_engine", "pp_reserve", "pp_particle_bonds", "pp_probe_bonds", "pp_add_remove", "pp_gc_step", "pp_patch_neighbours",
+               "pp_range_neighbours"]
 
 
 class GCResult(C.Structure):
@@ -152,6 +153,8 @@ def load_library():
     L.pp_probe_bonds.argtypes = [H, _dp, _dp, PI, PI]
     L.pp_add_remove.argtypes = [H, C.c_double, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(GCResult)]
     L.pp_gc_step.argtypes = [H, C.c_double, C.c_int, C.c_int, C.c_void_p, PI, PI]
+    L.pp_patch_neighbours.argtypes = [H, C.c_int, _ip, _ip, _ip]
+    L.pp_range_neighbours.argtypes = [H, C.c_int, _ip, C.c_int, _ip, _ip]
     _lib = L
     return L
 
@@ -213,9 +216,16 @@ class Engine:
             r, orient = np.zeros((1, 3)), np.zeros((1, 9))
         self._check(self.L.pp_upload(self.h, self.N, box, r, orient))
 
-    def download(self):
-        r = np.zeros((max(self.N, 1), 3))
-        m = np.zeros((max(self.N, 1), 9))
+    def download(self, out=None):
+        """positions and orientation matrices in the caller's particle order; out = (r[N, 3], orient[N, 9]) float64 arrays to fill
+        (pinned host memory makes the copy a DMA at PCIe speed; fresh pageable arrays otherwise)"""
+        if out is not None:
+            r, m = out
+            if r.shape[0] < self.N or m.shape[0] < self.N or r.dtype != np.float64 or m.dtype != np.float64:
+                raise ValueError("download: output arrays too small or not float64")
+        else:
+            r = np.zeros((max(self.N, 1), 3))
+            m = np.zeros((max(self.N, 1), 9))
         self._check(self.L.pp_download(self.h, r, m))
         return r[:self.N], m[:self.N].reshape(-1, 3, 3)
 
@@ -312,6 +322,23 @@ class Engine:
         self._check(self.L.pp_get_observables(self.h, C.byref(o), 0))
         self.N = int(o.N)
         return int(n.value), int(full.value)
+
+    # ---- neighbour queries of the cluster moves (avb.c:43-75, vmmc.c:148-229) ----------------------
+    def patch_neighbours(self, idx):
+        """-> (neighbours[n, 4]: bonded neighbour per patch or -1, num_neighbours[n])"""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        nb = np.full((max(len(idx), 1), 4), -1, dtype=np.int32)
+        num = np.zeros(max(len(idx), 1), dtype=np.int32)
+        self._check(self.L.pp_patch_neighbours(self.h, len(idx), idx, nb.reshape(-1), num))
+        return nb[:len(idx)], num[:len(idx)]
+
+    def range_neighbours(self, idx, max_per_particle=32):
+        """-> (counts[n], neighbours[n, max_per_particle]: particles with dist2 < (1 + delta)^2, -1 beyond the count)"""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        nb = np.full((max(len(idx), 1), max_per_particle), -1, dtype=np.int32)
+        cnt = np.zeros(max(len(idx), 1), dtype=np.int32)
+        self._check(self.L.pp_range_neighbours(self.h, len(idx), idx, int(max_per_particle), cnt, nb.reshape(-1)))
+        return cnt[:len(idx)], nb[:len(idx)]
 
     # ---- x-slab decomposition hooks (see slab.py) ------------------------------------------------
     def slab_setup(self, rank, world):

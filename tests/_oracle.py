@@ -247,6 +247,7 @@ def ref_lib():
     L.ref_bond_counts.argtypes = [_ip, _ip]
     L.ref_bond_lists.argtypes = [C.c_int, _ip, _ip]
     L.ref_rotate.argtypes = [_dp, _dp, C.c_double, _dp]
+    L.ref_patch_pairs.argtypes = [C.c_int, _ip, _ip, _ip, _ip]
     L.ref_eval_proposals.argtypes = [C.c_int, _ip, _dp, _dp, _dp, C.c_int, _ip, _ip, _ip]
     L.ref_run_moves.argtypes = [C.c_long]
     L.ref_run_steps.argtypes = [C.c_long]
@@ -343,6 +344,14 @@ class RefSystem:
         nb = np.full((max(self.N, 1), max_nb), -1, dtype=np.int32)
         self.L.ref_bond_lists(max_nb, c, nb.reshape(-1))
         return c[:self.N], nb[:self.N]
+
+    def patch_pairs(self, max_nb=8):
+        """Bonded neighbours with MC_interact's patch indices (onp, onq), over all pairs in ascending index."""
+        n = max(self.N, 1)
+        c = np.zeros(n, dtype=np.int32)
+        q, onp, onq = (np.full((n, max_nb), -1, dtype=np.int32) for _ in range(3))
+        self.L.ref_patch_pairs(max_nb, c, q.reshape(-1), onp.reshape(-1), onq.reshape(-1))
+        return c[:self.N], q[:self.N], onp[:self.N], onq[:self.N]
 
     def rotate(self, m_old, axis, theta):
         out = np.zeros(9)

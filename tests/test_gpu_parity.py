@@ -479,3 +479,64 @@ def test_gc_moves_golden(pp):
     b3, ov3, ok3 = e.check_energy()
     assert ok3 and ov3 == 0
     e.close()
+
+
+def test_bond_count_queue_overflow(pp, monkeypatch):
+    """K3: when more pairs pass the FP32 screens than the pair queue holds, the count is repeated with the exact tile kernel
+    (Counters.pad signals the overflow).  PP_BONDS_QUEUE_BYTES shrinks the queue to 511 pairs on a crystal with 900 bonds."""
+    g = load_golden("fcc")
+    delta, cosmax, T = g["params_a"]
+    e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    e.upload(g["box"], g["r"], g["orient"])
+    want = e.total_bonds()
+    assert want == (-int(g["energy_a"][0]), 0) and want[0] > 600
+    e.set_profiling(True)
+    e.reset_kernel_stats()
+    e.total_bonds()
+    normal = e.kernel_stats()["bonds"][0]
+    monkeypatch.setenv("PP_BONDS_QUEUE_BYTES", "4096")
+    e.reset_kernel_stats()
+    assert e.total_bonds() == want
+    assert e.kernel_stats()["bonds"][0] == normal + 2  # the streaming launches, then the tile kernel's two
+    monkeypatch.setenv("PP_BONDS_QUEUE_BYTES", "0")   # no queue at all: the tile kernel straight away
+    assert e.total_bonds() == want
+    e.close()
+
+
+def test_neighbour_queries_golden(pp):
+    """The neighbour queries of the cluster moves against the reference's own MC_interact over all pairs
+    (tests/golden/neighbour_queries.npz): bonded neighbour per patch as AVB's _set_neighbours collects it (avb.c:43-75) and the
+    particles within range as VMMC's _populate_possible_links meets them (vmmc.c:178)."""
+    g = load_golden("neighbour_queries")
+    delta, T = g["params"]
+    N = len(g["r"])
+    every = np.arange(N, dtype=np.int32)
+    for tag, cosmax in (("narrow", 0.98), ("wide", 0.8)):
+        e = pp.Engine(kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+        e.upload(g["box"], g["r"], g["orient"])
+        nb, num = e.patch_neighbours(every)
+        cnt, q, onp = g[f"{tag}_count"], g[f"{tag}_q"], g[f"{tag}_onp"]
+        assert np.array_equal(num, cnt)
+        for i in range(N):
+            for patch in range(4):
+                on_patch = [int(q[i, k]) for k in range(cnt[i]) if onp[i, k] == patch]
+                if not on_patch:
+                    assert nb[i, patch] == -1
+                elif len(on_patch) == 1:
+                    assert nb[i, patch] == on_patch[0]
+                else:  # two neighbours on one patch: which one stays depends on the traversal order (avb.c:64); one of them
+                    assert nb[i, patch] in on_patch
+        # a subset in another order gives the same rows
+        some = np.array([999, 3, 512, 3], dtype=np.int32)
+        nb2, num2 = e.patch_neighbours(some)
+        assert np.array_equal(nb2, nb[some]) and np.array_equal(num2, num[some])
+        e.close()
+    e = pp.Engine(kf_delta=delta, kf_cosmax=0.98, temperature=T)
+    e.upload(g["box"], g["r"], g["orient"])
+    cnt, nb = e.range_neighbours(every, 24)
+    assert np.array_equal(cnt, g["range_count"])
+    for i in range(N):
+        assert sorted(nb[i, :cnt[i]].tolist()) == sorted(g["range_nb"][i, :cnt[i]].tolist()) and np.all(nb[i, cnt[i]:] == -1)
+    cnt4, nb4 = e.range_neighbours(every, 4)  # a short list keeps the first ones in the same order
+    assert np.array_equal(cnt4, cnt) and np.array_equal(nb4, nb[:, :4])
+    e.close()

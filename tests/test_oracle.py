@@ -393,3 +393,29 @@ def test_gc_golden_fixture(oracle, tmp_path):
     for k in range(120):
         assert ref.add_remove(g["u"][k]) == (kind[k], acc[k], used[k], Ns[k], en[k]), f"move {k}"
     ref.close()
+
+
+def test_neighbour_queries_fixture(oracle, tmp_path):
+    """tests/golden/neighbour_queries.npz: symmetric (q lists p with the patches swapped), consistent with the bond counts of
+    warm1000.npz at the wide state point, every bonded pair inside the range lists; regenerated live where the reference is."""
+    g = load_golden("neighbour_queries")
+    w = load_golden("warm1000")
+    assert np.array_equal(g["wide_count"], w["bond_counts"])
+    for tag in ("narrow", "wide"):
+        cnt, q, onp, onq = g[f"{tag}_count"], g[f"{tag}_q"], g[f"{tag}_onp"], g[f"{tag}_onq"]
+        for i in range(len(cnt)):
+            for k in range(cnt[i]):
+                j = int(q[i, k])
+                assert i in q[j, :cnt[j]].tolist() and j in g["range_nb"][i, :g["range_count"][i]].tolist()
+                if tag == "narrow":  # one neighbour per patch: the pair is reported from the other side with the patches swapped
+                    kk = q[j, :cnt[j]].tolist().index(i)
+                    assert (onp[j, kk], onq[j, kk]) == (onq[i, k], onp[i, k])
+    if not oracle.have_ref():
+        return
+    rrr = str(tmp_path / "warm.rrr")
+    oracle.write_rrr(rrr, 0, g["box"], g["r"], g["orient"].reshape(-1, 9))
+    delta, T = g["params"]
+    ref = oracle.RefSystem(rrr, KF_delta=delta, KF_cosmax=0.8, Temperature=T)
+    c, q, onp, onq = ref.patch_pairs(8)
+    ref.close()
+    assert np.array_equal(c, g["wide_count"]) and np.array_equal(q, g["wide_q"]) and np.array_equal(onp, g["wide_onp"])

@@ -230,6 +230,34 @@ def gc_moves():
                         used=used, N=Ns, energies=en, r_final=r2, orient_final=m2)
 
 
+def neighbour_queries():
+    """tests/golden/neighbour_queries.npz: what the cluster moves ask of a configuration, from the reference's own MC_interact
+    over all pairs of the warm state: (narrow, KF_cosmax = 0.98 and wide, 0.8) bonded neighbours with the patch indices (onp, onq)
+    -- AVB's _set_neighbours (avb.c:43-75) -- and (KF_cosmax = -2: every pair inside the shell counts as bonded, MC.c:249-261) the
+    particles within the interaction range -- VMMC's possible links (vmmc.c:178)."""
+    g = np.load(os.path.join(GOLD, "warm1000.npz"))
+    tmp = "/tmp/_golden_warm.rrr"
+    O.write_rrr(tmp, 0, g["box"], g["r"], g["orient"].reshape(-1, 9))
+    out = {}
+    for tag, cosmax in (("narrow", 0.98), ("wide", 0.8)):
+        ref = O.RefSystem(tmp, **dict(WARM, KF_cosmax=cosmax))
+        r, m = ref.state()
+        c, q, onp, onq = ref.patch_pairs(8)
+        ref.close()
+        assert c.max() <= 8
+        out.update({f"{tag}_count": c, f"{tag}_q": q, f"{tag}_onp": onp, f"{tag}_onq": onq})
+        print("neighbour queries", tag, "bonds", int(c.sum()) // 2, "particles with two neighbours on one patch",
+              int(sum(len(set(onp[i, :c[i]])) < c[i] for i in range(len(c)))))
+    ref = O.RefSystem(tmp, **dict(WARM, KF_cosmax=-2.))
+    c, nb = ref.bond_lists(24)
+    e, ov = ref.total_energy()
+    ref.close()
+    assert ov == 0 and c.max() <= 24
+    print("neighbour queries: pairs in range", int(c.sum()) // 2, "most neighbours", int(c.max()))
+    np.savez_compressed(os.path.join(GOLD, "neighbour_queries.npz"), r=r, orient=m, box=g["box"],
+                        params=np.array([WARM["KF_delta"], WARM["Temperature"]]), range_count=c, range_nb=nb, **out)
+
+
 def helpers():
     """tests/golden/helpers.npz: the reference's random_vector_on_sphere (utils.c:115-131) fed with recorded uniforms
     (axis + number of uniforms consumed) and its gram_schmidt (utils.c:91-113) on perturbed orientation matrices."""
@@ -264,6 +292,8 @@ def main():
         return box_moves()
     if len(sys.argv) > 1 and sys.argv[1] == "gc_moves":
         return gc_moves()
+    if len(sys.argv) > 1 and sys.argv[1] == "neighbour_queries":
+        return neighbour_queries()
     one("fcc", os.path.join(REF, "fcc.rrr"), {"a": {}, "b": {"KF_cosmax": 0.92}}, n_prop=2048, T=0.11)
     one("bcc", os.path.join(REF, "bcc.rrr"), {"a": {}, "b": {"KF_delta": 0.135}}, n_prop=1024)
     tmp = "/tmp/_golden_gen.rrr"
@@ -277,6 +307,7 @@ def main():
     warm()
     box_moves()
     gc_moves()
+    neighbour_queries()
     helpers()
     known = {}
     for N, rho in [(32768, 0.3), (65536, 0.5)]:
