@@ -453,7 +453,8 @@ def measure(pkg, args, w, K, W, n_e2e, cpu_budget_s, ctx, headline):
     n_passes = 8 * n_prof
     passes_per_launch = max(int(round(n_passes / max(sweep_launches, 1))), 1)  # 1: a launch per colour pass; 4: a dataflow launch per half sweep
     per_launch_ms = sweep_ms / max(sweep_launches, 1)
-    tile_only = (n_local < 150000 and args.cells_max_occupancy < 0 and args.lanes != 1) or min(cells) < 4
+    dense = args.cells_max_occupancy < 0 and args.lanes != 1 and 27. * N > 32. * cells[0] * cells[1] * cells[2]  # routing_limits (pp_api.cu)
+    tile_only = (n_local < 150000 and args.cells_max_occupancy < 0 and args.lanes != 1) or min(cells) < 4 or dense
     sweep_kernel = ("k_sweep_pass (tile kernel)" if tile_only else
                     "k_sweep_half (the four colour passes of a half sweep in one dataflow launch; 8 / 4 / 1 lanes per cell)" if passes_per_launch == 4 else
                     "k_sweep_fused (8 / 4 / 1 lanes per cell in one launch)")
@@ -462,14 +463,17 @@ def measure(pkg, args, w, K, W, n_e2e, cpu_budget_s, ctx, headline):
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     cell_builds = max(stats["cells"][0] // 10, 1)
     n_bonds = max(stats["bonds"][0], 1)
+    # a full count is three launches (zero, FP32 screen, FP64 on the queued pairs) on a grid with four or more cells per axis, else two
+    per_count = 3 if min(cells) >= 4 else 2
+    ms_per_count = stats["bonds"][1] / max(stats["bonds"][0] / per_count, 1.)
     kernels = {
         "sweep_pass": {"launches": sweep_launches, "passes": n_passes, "ms_per_launch": per_launch_ms, "ms_per_pass": sweep_ms / n_passes,
                        "alg_bytes_per_launch": bytes_per_launch, "GBps": achieved},
         "cell_build": {"launches": stats["cells"][0], "builds": cell_builds, "ms_per_build": stats["cells"][1] / cell_builds,
                        "GBps": CELLS_BYTES_PER_PARTICLE * n_local / (max(stats["cells"][1], 1e-9) / cell_builds * 1e-3) / 1e9},
         "proposals": {"launches": stats["rng"][0], "ms_per_launch": stats["rng"][1] / max(stats["rng"][0], 1)},
-        "bond_count": {"launches": stats["bonds"][0], "ms_per_launch": stats["bonds"][1] / n_bonds,
-                       "GBps": BONDS_BYTES_PER_PARTICLE * n_owned / (max(stats["bonds"][1] / n_bonds, 1e-9) * 1e-3) / 1e9},
+        "bond_count": {"launches": stats["bonds"][0], "ms_per_launch": stats["bonds"][1] / n_bonds, "ms_per_count": ms_per_count,
+                       "GBps": BONDS_BYTES_PER_PARTICLE * n_owned / (max(ms_per_count, 1e-9) * 1e-3) / 1e9},
     }
     if stats["rescale"][0]:
         n_rs = stats["rescale"][0]

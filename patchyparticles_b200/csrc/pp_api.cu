@@ -173,6 +173,10 @@ void routing_limits(const pp_handle *h, int *m1, int *m2) {
 	}
 	else if(h->prm.lanes_per_cell != 0) return; // an explicit tile width alone: tile kernel only
 	else {
+		// a dense system (a crystal, a compressed liquid): the mean neighbourhood does not fit the staging area of the thread-per-cell
+		// configuration, nearly every cell would run on 8 lanes -- the tile kernel, which stages 64 neighbours per cell, is 2.2x faster
+		// there (FCC at N = 256000: 4.8e8 against 2.2e8 attempts/s, profiles/README.md)
+		if(h->n_cells > 0 && 27. * (double) h->N > (double) kCellsNbCap * (double) h->n_cells) return;
 		// measured on B200 (profiles/README.md)
 		*m1 = (h->N >= 800000) ? 3 : ((h->N >= 400000) ? 2 : ((h->N >= 150000) ? 1 : 0));
 		*m2 = (h->N >= 800000) ? 3 : ((h->N >= 400000) ? 3 : ((h->N >= 150000) ? 2 : 0));
@@ -533,7 +537,16 @@ static int upload_finish(pp_handle *h, int n, bool check_held, bool keep_books) 
 		memset(h->accepted, 0, sizeof(h->accepted));
 	}
 	memset(&h->bm, 0, sizeof(h->bm));
-	if(ensure_cells_valid(h)) return 1;
+	if(h->slab_world > 1) {
+		if(ensure_cells_valid(h)) return 1; // (a slab engine keeps only the particles of its layers: the sort tells which)
+	}
+	else {
+		// single engine: the grid is fixed here (a box too small for it is refused now), the counting sort waits for the first
+		// consumer -- a sweep re-sorts on its shifted grid anyway, so an upload followed by a sweep builds the cells once, not twice
+		if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", h->box[0], h->box[1], h->box[2], h->r_cut);
+		h->nxl = h->n_side[0];
+		h->n_cells = h->nxl * h->n_side[1] * h->n_side[2];
+	}
 	CUDA_OK(h, cudaStreamSynchronize(h->stream));
 	if(h->slab_world > 1 && check_held && h->N != n)
 		return fail(h, "upload: %d of the %d particles lie outside the layers this engine holds", n - h->N, n);

@@ -202,8 +202,9 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 			const double4 *own_pos = own_staged ? &os.pos[pick] : pos + sp;
 			const double *own_ori = own_staged ? os.ori + 9 * pick : ori + 9ll * sp;
 			if(is_owner) tl.tries++;
-			if(!staged) { // neighbourhood larger than the staging area (dense packing): serial FP64 path
-				if(is_owner) trial_serial(sc, cell_start, pos, ori, posf, proposals + first + t, cell, ix, iy, iz, sp, tl, hm, hm_off);
+			if(!staged) { // neighbourhood larger than the staging area (dense packing): FP64 walk of the 27 cells, shared by the group's lanes
+				if(G == 1) trial_serial(sc, cell_start, pos, ori, posf, proposals + first + t, cell, ix, iy, iz, sp, tl, hm, hm_off);
+				else trial_group<G>(sc, cell_start, pos, ori, posf, proposals + first + t, cell, ix, iy, iz, sp, tl, hm, hm_off, gl, gmask, is_owner);
 				continue;
 			}
 			const double dx = pr->dx, dy = pr->dy, dz = pr->dz;

@@ -148,6 +148,9 @@ class SlabEngine:
     def upload(self, box, r, orient):
         """Every rank is handed the whole configuration and takes only the particles of the layers it holds (owned + halo):
         pp_upload_select, on the GPU when the arrays are pinned host memory."""
+        import time
+        timing = os.environ.get("PP_SLAB_TIMING") and self.rank == 0
+        t = [time.perf_counter()]
         r = np.asarray(r, dtype=np.float64).reshape(-1, 3)
         orient = np.asarray(orient, dtype=np.float64).reshape(-1, 9)
         self.N = int(r.shape[0])
@@ -158,16 +161,22 @@ class SlabEngine:
                 self.eng.slab_peer_close()
                 dist.barrier()
                 self._connected = False
+        t.append(time.perf_counter())
         if hasattr(self.eng, "upload_select"):
             self.eng.upload_select(box, r, orient)
             self.h2d_bytes = int(r.nbytes + 108 * self.eng.slab_range()[3])  # every position + the selected particles' state
         else:  # stand-in engines of the CPU tests
             self.eng.upload(box, r, orient)
             self.h2d_bytes = 0
+        t.append(time.perf_counter())
         self._halo_cache = [None, None]
         self._rebuilds = 0
         if self.peer_halo:
             self._connect_peers()
+        t.append(time.perf_counter())
+        if timing:
+            print(f"[slab upload] close {1e3 * (t[1] - t[0]):.2f} ms, select + copy + cell build {1e3 * (t[2] - t[1]):.2f} ms, "
+                  f"connect {1e3 * (t[3] - t[2]):.2f} ms", file=sys.stderr, flush=True)
 
     def _connect_peers(self):
         """Every engine exports the description of its device state (CUDA IPC) and maps those of its ring neighbours."""
