@@ -36,14 +36,24 @@ constexpr int kStageCap = 64; // staged neighbours per cell; denser neighbourhoo
 // ---------------------------------------------------------------------------------------------
 // K2a: proposals
 // ---------------------------------------------------------------------------------------------
+static_assert(sizeof(Proposal) == 7 * 16, "k_make_proposals copies its records out as seven 16-byte words each");
 __global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ SimConst sc, const int *__restrict__ cell_start,
 		const int *__restrict__ cell_sorted, Proposal *__restrict__ out) {
+	// the 112-byte records of a block leave through shared memory: 16-byte stores of consecutive lanes to consecutive addresses
+	// instead of seven stores of stride 112 per thread
+	__shared__ __align__(16) Proposal s_out[128];
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= sc.N) return;
-	const int lcell = cell_sorted[i];
-	const int nyz = sc.n_side[1] * sc.n_side[2];
-	const int lx = lcell / nyz, ly = (lcell - lx * nyz) / sc.n_side[2], lz = lcell - lx * nyz - ly * sc.n_side[2];
-	if(lx < sc.own_lo || lx >= sc.own_hi) return; // halo particle: moved by its owner
+	bool mine = i < sc.N;
+	int lcell = 0, lx = 0, ly = 0, lz = 0;
+	if(mine) {
+		lcell = cell_sorted[i];
+		const int nyz = sc.n_side[1] * sc.n_side[2];
+		lx = lcell / nyz;
+		ly = (lcell - lx * nyz) / sc.n_side[2];
+		lz = lcell - lx * nyz - ly * sc.n_side[2];
+		mine = lx >= sc.own_lo && lx < sc.own_hi; // halo particle: moved by its owner (its record is never read)
+	}
+	if(mine) {
 	const int first = cell_start[lcell];
 	const int n_here = cell_start[lcell + 1] - first;
 	const int t = i - first;
@@ -93,7 +103,17 @@ __global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ 
 	pr.R[6] = __dsub_rn(xz, ys);
 	pr.R[7] = __dadd_rn(yz, xs);
 	pr.R[8] = __dadd_rn(zz, __dmul_rn(__dsub_rn(1., zz), ct));
-	out[i] = pr;
+	s_out[threadIdx.x] = pr;
+	}
+	else s_out[threadIdx.x] = Proposal{};
+	__syncthreads();
+	{
+		const long long base = (long long) blockIdx.x * blockDim.x; // first record of the block
+		const int n_rec = (int) min((long long) blockDim.x, (long long) sc.N - base);
+		const uint4 *src = reinterpret_cast<const uint4 *>(s_out);
+		uint4 *dst = reinterpret_cast<uint4 *>(out + base);
+		for(int k = threadIdx.x; k < 7 * n_rec; k += blockDim.x) dst[k] = src[k]; // (sizeof(Proposal) = 7 x 16)
+	}
 }
 
 int launch_proposals_for_sweep(const SimConst &sc, const CellBuffers &cb, Proposal *proposals, cudaStream_t st) {
