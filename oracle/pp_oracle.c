@@ -535,6 +535,103 @@ static double u32_to_unit(uint32_t x) {
 	return ((double) x + 0.5) * (1.0 / 4294967296.0);
 }
 
+/* ------------------------------------------------------------------ grand-canonical insertion / removal */
+/* random_vector_on_sphere (utils.c:115-131) from a recorded stream */
+static void gc_sphere(const double *u, int n_u, int *used, double *res) {
+	double ran1, ran2, ransq;
+	do {
+		ran1 = 1. - 2. * (*used < n_u ? u[(*used)++] : 0.75);
+		ran2 = 1. - 2. * (*used < n_u ? u[(*used)++] : 0.75);
+		ransq = ran1 * ran1 + ran2 * ran2;
+	} while(ransq >= 1. && *used < n_u);
+	const double ranh = 2. * sqrt(1. - ransq);
+	res[0] = ran1 * ranh;
+	res[1] = ran2 * ranh;
+	res[2] = 1. - 2. * ransq;
+}
+
+/* MC_add_remove (MC.c:342-448) with the uniforms the reference would draw, in its order.  Returns the kind of move (2 insertion,
+ * 3 removal, -1 returned before a try); *accepted, *used (uniforms consumed); *energy_bonds is the running bond count.  A new
+ * particle gets index N; when particle p leaves, the last one takes its index (MC.c:414-438). */
+int ppo_add_remove(ppo_system *s, double z, int n_min, int n_max, const double *u, int n_u, int *accepted, int *used, long long *energy_bonds) {
+	int k, ov;
+	*accepted = 0;
+	*used = 0;
+	if(u[(*used)++] < 0.5) { /* MC.c:344 */
+		double r[3], x[3], y[3], zz[3], m[9], pp[12];
+		if(s->N == n_max) return -1;
+		for(k = 0; k < 3; k++) r[k] = u[(*used)++] * s->box[k]; /* MC.c:352-354 */
+		/* random_orientation (utils.c:133-169): three points, Gram-Schmidt, rows (z, x, y), first two swapped if det < 0 */
+		gc_sphere(u, n_u, used, x);
+		gc_sphere(u, n_u, used, y);
+		gc_sphere(u, n_u, used, zz);
+		{
+			double g[9];
+			memcpy(g, x, sizeof(x));
+			memcpy(g + 3, y, sizeof(y));
+			memcpy(g + 6, zz, sizeof(zz));
+			ppo_gram_schmidt(g);
+			memcpy(x, g, sizeof(x));
+			memcpy(y, g + 3, sizeof(y));
+			memcpy(zz, g + 6, sizeof(zz));
+		}
+		memcpy(m, zz, sizeof(zz));
+		memcpy(m + 3, x, sizeof(x));
+		memcpy(m + 6, y, sizeof(y));
+		{
+			double det = 0.;
+			det += m[0] * m[4] * m[8];
+			det += m[1] * m[5] * m[6];
+			det += m[2] * m[3] * m[7];
+			det -= m[2] * m[4] * m[6];
+			det -= m[0] * m[5] * m[7];
+			det -= m[1] * m[3] * m[8];
+			if(det < 0) {
+				memcpy(m, x, sizeof(x));
+				memcpy(m + 3, zz, sizeof(zz));
+			}
+		}
+		patches_from(s->base, m, pp);
+		const int bonds = probe_bonds(s, -1, r, pp, &ov, NULL);          /* MC.c:361 */
+		const double delta_E = -(double) bonds;
+		const double acc = exp(-delta_E / s->T) * z * s->V / (s->N + 1.); /* MC.c:362 */
+		if(!ov && u[(*used)++] < acc) {                                   /* MC.c:364 */
+			const size_t n = (size_t) s->N + 1;
+			s->r = realloc(s->r, n * 3 * sizeof(double));
+			s->m = realloc(s->m, n * 9 * sizeof(double));
+			s->patches = realloc(s->patches, n * 12 * sizeof(double));
+			memcpy(s->r + 3 * s->N, r, sizeof(r));
+			memcpy(s->m + 9 * s->N, m, sizeof(m));
+			memcpy(s->patches + 12 * s->N, pp, sizeof(pp));
+			s->N++;
+			*energy_bonds += bonds;
+			cells_build(s);
+			*accepted = 1;
+		}
+		return 2;
+	}
+	if(s->N == n_min) return -1;
+	{
+		const int p = (int) (u[(*used)++] * s->N);                       /* MC.c:383 */
+		const int bonds = ppo_particle_bonds(s, p, &ov);
+		const double delta_E = (double) bonds;
+		const double acc = exp(-delta_E / s->T) * s->N / (s->V * z);     /* MC.c:386 */
+		if(u[(*used)++] < acc) {
+			const int q = s->N - 1;
+			if(p != q) {
+				memcpy(s->r + 3 * p, s->r + 3 * q, 3 * sizeof(double));
+				memcpy(s->m + 9 * p, s->m + 9 * q, 9 * sizeof(double));
+				patches_from(s->base, s->m + 9 * p, s->patches + 12 * p);   /* MC.c:428-430 */
+			}
+			s->N--;
+			*energy_bonds -= bonds;
+			cells_build(s);
+			*accepted = 1;
+		}
+		return 3;
+	}
+}
+
 void ppo_even_grid(const double *box, double r_cut, int *n_side) {
 	int k;
 	for(k = 0; k < 3; k++) {

@@ -3,7 +3,7 @@
  *
  * CPU restatement (plain C, FP64, no FMA contraction) of the PatchyParticles hot path:
  * Kern-Frenkel pair test, per-particle and total bond counts over cell lists, roto-translation
- * proposal evaluation with the reference's Metropolis rule, volume / Lx move arithmetic, and a
+ * proposal evaluation with the reference's Metropolis rule, volume / Lx move arithmetic, insertion / removal, and a
  * serial restatement of this repo's checkerboard sweep (same Philox streams as the CUDA kernel).
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  *
@@ -74,6 +74,9 @@ int ppo_volume_move(ppo_system *s, double P, double rescale_factor_max, double u
 /* Lx move (MC.c:515-585) given its two uniforms; returns 1 accepted, 0 rejected, -1 early reject */
 int ppo_Lx_move(ppo_system *s, double Lx_change_max, double Lyz_min, double Lyz_max, int faithful_sign,
 		double u_lx, double u_acc, long long *energy_bonds, int *overlap_out);
+
+/* MC_add_remove (MC.c:342-448) given its uniforms in the reference's draw order; returns 2 (insertion), 3 (removal) or -1 */
+int ppo_add_remove(ppo_system *s, double z, int n_min, int n_max, const double *u, int n_u, int *accepted, int *used, long long *energy_bonds);
 
 /* ---- serial restatement of this repo's checkerboard sweep ----------------------------- */
 typedef struct {

@@ -74,6 +74,8 @@ def port_lib():
                                   C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.ppo_Lx_move.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                               C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    L.ppo_add_remove.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_longlong)]
     L.ppo_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double,
                             C.POINTER(C.c_longlong), C.POINTER(SweepStats)]
     L.ppo_even_grid.argtypes = [_dp, C.c_double, _ip]
@@ -198,6 +200,14 @@ class PortSystem:
         acc = self.L.ppo_Lx_move(self.h, Lx_change_max, Lyz_min, Lyz_max, int(faithful_sign), u_lx, u_acc,
                                  C.byref(b), C.byref(ov))
         return int(acc), int(b.value), int(ov.value)
+
+    def add_remove(self, z, n_min, n_max, uniforms, bonds):
+        """MC_add_remove (MC.c:342-448) with recorded uniforms -> (kind, accepted, uniforms consumed, N, running bonds)"""
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        a, used, b = C.c_int(0), C.c_int(0), C.c_longlong(bonds)
+        kind = self.L.ppo_add_remove(self.h, float(z), int(n_min), int(n_max), u, int(u.size), C.byref(a), C.byref(used), C.byref(b))
+        self.N = int(self.L.ppo_N(self.h))
+        return int(kind), int(a.value), int(used.value), self.N, int(b.value)
 
     def sweep(self, seed, sweep_index, disp_max, theta_max, bonds, stats=None, shift_every=4):
         b = C.c_longlong(bonds)

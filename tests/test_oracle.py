@@ -419,3 +419,19 @@ def test_neighbour_queries_fixture(oracle, tmp_path):
     c, q, onp, onq = ref.patch_pairs(8)
     ref.close()
     assert np.array_equal(c, g["wide_count"]) and np.array_equal(q, g["wide_q"]) and np.array_equal(onp, g["wide_onp"])
+
+
+def test_port_gc_moves_golden(oracle):
+    """The restated MC_add_remove against the reference's own (tests/golden/gc_moves.npz): every decision, the uniforms consumed,
+    N and the running energy after each of the 400 moves, and the final configuration index for index, bit for bit."""
+    g = load_golden("gc_moves")
+    delta, cosmax, T, z, n_min, n_max = g["params"]
+    p = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+    bonds, ov = p.total_bonds()
+    assert (-bonds, ov) == (g["energy0"][0], 0)
+    for k in range(len(g["u"])):
+        kind, acc, used, N, bonds = p.add_remove(z, int(n_min), int(n_max), g["u"][k], bonds)
+        assert (kind, acc, used, N, -bonds) == (g["kind"][k], g["accepted"][k], g["used"][k], g["N"][k], g["energies"][k]), f"move {k}"
+    r, m = p.state()
+    assert np.array_equal(r, g["r_final"]) and np.array_equal(m, g["orient_final"])
+    assert p.total_bonds() == (bonds, 0)
