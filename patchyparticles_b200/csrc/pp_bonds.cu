@@ -330,7 +330,7 @@ int launch_total_bonds(const SimConst &sc, const int *cell_start, const int *cel
 		if(cap > kPencilMaxCap) cap = kPencilMaxCap;
 		const double own = occ * seg_cells; // particles of a block
 		// a grid that fits the machine at once is latency bound: the widest block brings the bounds and the shadows in the fewest rounds
-		const bool small = n_pencils * n_seg <= 148 * 10;
+		const bool small = n_pencils * n_seg * kPencilMaxThreads <= 148 * 2048; // (every block resident at once even at full width)
 		const int threads = small ? kPencilMaxThreads : (own <= 26. ? 32 : (own <= 56. ? 64 : (own <= 84. ? 96 : kPencilMaxThreads)));
 		const size_t smem = sizeof(uint4) * 5 * cap + sizeof(int2) * kPencilQueue + sizeof(int) * 5 * (kPencilMaxCells + 3);
 		k_bonds_screen<<<(unsigned) (n_pencils * n_seg), threads, smem, st>>>(sc, cell_start, cell_sorted, ori, posf, counters, queue, queue_cap, seg_cells,

@@ -409,13 +409,22 @@ __device__ __forceinline__ void mirror_state(const HaloMirror &hm, int off_l, in
 		d = sp - hm.ls3;
 	}
 	else return;
+	// eight stores over NVLink instead of fourteen: 16-byte words wherever the alignment allows
 	double *q = reinterpret_cast<double *>(tp + d); // x, y, z; the id in .w stays
-	q[0] = p.x;
-	q[1] = p.y;
+	*reinterpret_cast<double2 *>(q) = make_double2(p.x, p.y);
 	q[2] = p.z;
-	store_shadow_xyz(tf + d, shadow);
+	tf[d] = make_uint4(shadow.x, shadow.y, shadow.z, (unsigned) d); // (.w: the slot on the neighbour's side, which is d)
+	double *o = to + 9ll * d; // 72-byte records: 16-byte aligned for even d
+	if((d & 1) == 0) {
 #pragma unroll
-	for(int k = 0; k < 9; k++) to[9ll * d + k] = m[k];
+		for(int k = 0; k < 8; k += 2) *reinterpret_cast<double2 *>(o + k) = make_double2(m[k], m[k + 1]);
+		o[8] = m[8];
+	}
+	else {
+		o[0] = m[0];
+#pragma unroll
+		for(int k = 1; k < 9; k += 2) *reinterpret_cast<double2 *>(o + k) = make_double2(m[k], m[k + 1]);
+	}
 }
 
 __device__ __forceinline__ int mirror_offset(const HaloMirror &hm) {
