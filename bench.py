@@ -42,6 +42,10 @@ WORKLOADS = {
     "256k": dict(N=262144, rho=0.5, T=0.1, kind="fluid", extra={}),
     "512k": dict(N=524288, rho=0.6, T=0.1, kind="fluid", extra={}),
     "1M": dict(N=1048576, rho=0.6, T=0.1, kind="fluid", extra={}),
+    "448k": dict(N=458752, rho=0.6, T=0.1, kind="fluid", extra={}),
+    "576k": dict(N=589824, rho=0.6, T=0.1, kind="fluid", extra={}),
+    "640k": dict(N=655360, rho=0.6, T=0.1, kind="fluid", extra={}),
+    "768k": dict(N=786432, rho=0.6, T=0.1, kind="fluid", extra={}),
     "npt32k": dict(N=32768, rho=0.3, T=0.15, kind="fluid", extra=dict(ensemble=5, P=0.5, rescale_factor_max=1e-3)),
     "lx32k": dict(N=32768, rho=0.3, T=0.15, kind="fluid", extra=dict(Lx_move=1, Lx_change_max=0.01, Lyz_min=20., Lyz_max=80.)),
     "fcc256k": dict(N=256000, rho=1.041, T=0.11, kind="fcc", extra={}),
@@ -335,6 +339,9 @@ class Arm:
         self.sharded = sharded
         if sharded:
             from patchyparticles_b200.slab import SlabEngine
+            # every slab the same number of x layers (170 -> 168 layers on 2 and 4 GPUs, 160 on 8): no engine carries more than its share, and
+            # the fused pass of an engine stays inside one resident wave of blocks (profiles/r03h_one_wave.txt)
+            params["x_layers_multiple"] = 2 * world
             self.drv = SlabEngine(rank, world, local_rank, seed=SEED, **params)
             self.eng = self.drv.eng
         else:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 3
+#define PP_ABI_VERSION 4
 
 /* move-type slots of System.tries[] / accepted[] (defs.h:11-19) */
 #define PP_N_MOVES 8
@@ -71,6 +71,9 @@ typedef struct pp_params {
 	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
 	int cells_mid_occupancy;    /* cells with more particles than cells_max_occupancy and at most this many run on 4 lanes per cell, the
 	                               more crowded ones on 8; -1 = automatic */
+	int x_layers_multiple;      /* the number of cell layers along x is rounded down to a multiple of this (even) number; 0 = 2 (any even
+	                               grid).  2 n for a run in n x-slabs gives every slab the same number of layers; a single engine given the
+	                               same value follows the same trajectory */
 } pp_params;
 
 typedef struct pp_observables {

@@ -208,7 +208,7 @@ int build_cells(pp_handle *h, const SimConst &sc, const StateView &src, const St
 // compressing run goes on instead of aborting.
 bool box_too_small(pp_handle *h, const double *nb) {
 	int ns[3];
-	if(even_grid(nb, h->r_cut, ns) == 0) return false;
+	if(even_grid(nb, h->r_cut, ns, h->prm.x_layers_multiple) == 0) return false;
 	h->small_box_rejections++;
 	return true;
 }
@@ -240,11 +240,14 @@ void peer_release(pp_handle *h) {
 
 // even grid with cells of side >= r_cut (cells.c:22-28 uses floor(box / r_cut), any parity)
 // the 1e-9 margin keeps non-adjacent cells more than r_cut apart whatever the rounding of the cell index
-int even_grid(const double *box, double r_cut, int *n_side) {
+// x_multiple (pp_params.x_layers_multiple, even; 0 or 2: none): the number of x layers is rounded down to a multiple of it -- 2 n for a
+// run in n slabs gives every slab the same number of layers.  Any even grid with cells of side >= r_cut finds the same pairs.
+int even_grid(const double *box, double r_cut, int *n_side, int x_multiple) {
 	for(int k = 0; k < 3; k++) {
 		int n = (int) floor(box[k] / r_cut);
 		n &= ~1;
 		if(n >= 2 && box[k] / n < r_cut * (1. + 1e-9)) n -= 2;
+		if(k == 0 && x_multiple > 2 && n >= x_multiple) n -= n % x_multiple; // (a box too small for one period of it keeps the plain even grid)
 		if(n < 2) return 1;
 		n_side[k] = n;
 	}
@@ -382,7 +385,7 @@ int sort_into(pp_handle *h, const double *shift, const StateView &src, const Sta
 // K1 on the current state with the given grid shift; the sorted copy becomes current.
 int rebin(pp_handle *h, const double *shift) {
 	if(h->slab_world <= 1) {
-		if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", h->box[0], h->box[1], h->box[2], h->r_cut);
+		if(even_grid(h->box, h->r_cut, h->n_side, h->prm.x_layers_multiple)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", h->box[0], h->box[1], h->box[2], h->r_cut);
 		h->nxl = h->n_side[0];
 	}
 	h->n_cells = h->nxl * h->n_side[1] * h->n_side[2];
@@ -495,7 +498,7 @@ static int upload_begin(pp_handle *h, int N_global, const double *box, bool keep
 	h->N_global = N_global;
 	memcpy(h->box, box, sizeof(h->box));
 	if(!keep_books) h->V = box[0] * box[1] * box[2];
-	if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", box[0], box[1], box[2], h->r_cut);
+	if(even_grid(h->box, h->r_cut, h->n_side, h->prm.x_layers_multiple)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", box[0], box[1], box[2], h->r_cut);
 	h->nxl = h->n_side[0];
 	if(h->slab_world > 1) {
 		if(h->n_side[0] / 2 < h->slab_world) return fail(h, "%d x layers cannot be split over %d engines (at least 2 layers each)", h->n_side[0], h->slab_world);
@@ -543,7 +546,7 @@ static int upload_finish(pp_handle *h, int n, bool check_held, bool keep_books) 
 	else {
 		// single engine: the grid is fixed here (a box too small for it is refused now), the counting sort waits for the first
 		// consumer -- a sweep re-sorts on its shifted grid anyway, so an upload followed by a sweep builds the cells once, not twice
-		if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", h->box[0], h->box[1], h->box[2], h->r_cut);
+		if(even_grid(h->box, h->r_cut, h->n_side, h->prm.x_layers_multiple)) return fail(h, "box (%g, %g, %g) is smaller than two cells of side r_cut = %g", h->box[0], h->box[1], h->box[2], h->r_cut);
 		h->nxl = h->n_side[0];
 		h->n_cells = h->nxl * h->n_side[1] * h->n_side[2];
 	}
@@ -692,7 +695,7 @@ int box_trial_local(pp_handle *h, long long *bonds_local, int *overlap_local, in
 	if(!h->bonds_known) return fail(h, "box move before the initial pp_total_bonds");
 	if(ensure_cells_valid(h)) return 1;
 	int ns[3];
-	bool regrid = even_grid(bm.nb, h->r_cut, ns) != 0;
+	bool regrid = even_grid(bm.nb, h->r_cut, ns, h->prm.x_layers_multiple) != 0;
 	for(int k = 0; k < 3 && !regrid; k++) regrid = (bm.nb[k] / h->n_side[k] < h->r_cut * (1. + 1e-9));
 	if(regrid && h->slab_world > 1) {
 		*status = 2;
@@ -804,6 +807,7 @@ void pp_default_params(pp_params *p) {
 	p->lanes_per_cell = 0;
 	p->cells_max_occupancy = -1;
 	p->cells_mid_occupancy = -1;
+	p->x_layers_multiple = 0;
 }
 
 const char *pp_last_error(const pp_handle *h) {
@@ -820,6 +824,7 @@ int pp_create(const pp_params *params, pp_handle **out) {
 	*out = h; // returned even on failure so that the caller can read pp_last_error
 	if(params->ensemble != PP_NVT && params->ensemble != PP_NPT) return fail(h, "Ensemble %d not supported on the GPU path (0 = NVT, 5 = NPT)", params->ensemble);
 	if(params->ensemble == PP_NPT && params->Lx_move) return fail(h, "Lx_move is only available with Ensemble = 0 (as in the reference, system.c:165-171)");
+	if(params->x_layers_multiple < 0 || (params->x_layers_multiple & 1)) return fail(h, "x_layers_multiple must be an even number (0: any even grid)");
 	if(!(params->temperature > 0.)) return fail(h, "Temperature must be positive");
 	int n_dev = 0;
 	cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -968,7 +973,7 @@ int pp_upload_select(pp_handle *h, int N, const double *box, const double *r, co
 int pp_slab_select(const pp_params *params, int rank, int world, int N, const double *box, const double *r, unsigned char *mine) {
 	if(params == nullptr || box == nullptr || (N > 0 && (r == nullptr || mine == nullptr)) || world < 1 || rank < 0 || rank >= world) return 1;
 	int n_side[3];
-	if(even_grid(box, 1. + params->kf_delta, n_side)) return 1;
+	if(even_grid(box, 1. + params->kf_delta, n_side, params->x_layers_multiple)) return 1;
 	if(world == 1) {
 		memset(mine, 1, (size_t) N);
 		return 0;
@@ -1066,7 +1071,7 @@ int pp_sweep(pp_handle *h, long long nsteps) {
 		// lists stay valid because accepted moves never leave their cell
 		const long long period = h->prm.shift_every;
 		if(!h->sweep_grid || !h->cells_valid || h->step % period == 0) {
-			if(even_grid(h->box, h->r_cut, h->n_side)) return fail(h, "box too small for the checkerboard");
+			if(even_grid(h->box, h->r_cut, h->n_side, h->prm.x_layers_multiple)) return fail(h, "box too small for the checkerboard");
 			double shift[3];
 			sweep_shift(h->prm.seed, (uint64_t) (h->step / period), h->box, h->n_side, shift);
 			if(rebin(h, shift)) return 1;

@@ -250,7 +250,7 @@ int group_box_move(pp_group *g, int kind, const double *u, int *accepted) {
 int regrid_if_needed(pp_group *g) {
 	int ns[3];
 	pp_handle *h0 = g->h[0];
-	if(even_grid(h0->box, h0->r_cut, ns)) return gfail(g, "box too small for the checkerboard");
+	if(even_grid(h0->box, h0->r_cut, ns, h0->prm.x_layers_multiple)) return gfail(g, "box too small for the checkerboard");
 	if(ns[0] == h0->n_side[0] && ns[1] == h0->n_side[1] && ns[2] == h0->n_side[2]) return 0;
 	const double one[3] = {1., 1., 1.};
 	const double V = h0->V;

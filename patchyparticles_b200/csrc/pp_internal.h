@@ -128,7 +128,7 @@ pp::SimConst make_const(const pp_handle *h, const double *box, const double *shi
 pp::StateView view(pp_handle *h, int p, int o);
 void prof_begin(pp_handle *h);
 void prof_end(pp_handle *h, int kclass, int n_launches);
-int even_grid(const double *box, double r_cut, int *n_side);
+int even_grid(const double *box, double r_cut, int *n_side, int x_multiple);
 int rebin(pp_handle *h, const double *shift);
 int ensure_cells_valid(pp_handle *h);
 int fetch_counters(pp_handle *h);

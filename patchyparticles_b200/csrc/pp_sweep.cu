@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ 
 	// the 112-byte records of a block leave through shared memory: 16-byte stores of consecutive lanes to consecutive addresses
 	// instead of seven stores of stride 112 per thread
 	__shared__ __align__(16) Proposal s_out[128];
+	__shared__ unsigned char s_mine[128];
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool mine = i < sc.N;
 	int lcell = 0, lx = 0, ly = 0, lz = 0;
@@ -105,14 +106,15 @@ __global__ void __launch_bounds__(128) k_make_proposals(const __grid_constant__ 
 	pr.R[8] = __dadd_rn(zz, __dmul_rn(__dsub_rn(1., zz), ct));
 	s_out[threadIdx.x] = pr;
 	}
-	else s_out[threadIdx.x] = Proposal{};
+	s_mine[threadIdx.x] = mine;
 	__syncthreads();
 	{
 		const long long base = (long long) blockIdx.x * blockDim.x; // first record of the block
 		const int n_rec = (int) min((long long) blockDim.x, (long long) sc.N - base);
 		const uint4 *src = reinterpret_cast<const uint4 *>(s_out);
 		uint4 *dst = reinterpret_cast<uint4 *>(out + base);
-		for(int k = threadIdx.x; k < 7 * n_rec; k += blockDim.x) dst[k] = src[k]; // (sizeof(Proposal) = 7 x 16)
+		for(int k = threadIdx.x; k < 7 * n_rec; k += blockDim.x) // (sizeof(Proposal) = 7 x 16)
+			if(s_mine[k / 7]) dst[k] = src[k]; // (a halo particle's record is never read: not written either, it would only take room in L2)
 	}
 }
 

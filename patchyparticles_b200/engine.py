@@ -29,7 +29,7 @@ class Params(C.Structure):
                 ("Lx_change_max", C.c_double), ("Lyz_min", C.c_double), ("Lyz_max", C.c_double),
                 ("Lx_reference_sign", C.c_int), ("seed", C.c_uint64), ("device", C.c_int),
                 ("lanes_per_cell", C.c_int), ("cell_lanes", C.c_int), ("cells_max_occupancy", C.c_int),
-                ("shift_every", C.c_int), ("cells_mid_occupancy", C.c_int)]
+                ("shift_every", C.c_int), ("cells_mid_occupancy", C.c_int), ("x_layers_multiple", C.c_int)]
 
 
 class Observables(C.Structure):
@@ -169,7 +169,7 @@ class Engine:
     def __init__(self, ensemble=NVT, temperature=0.1, disp_max=0.1, theta_max=0.1, kf_delta=0.119, kf_cosmax=0.98,
                  P=0.0, rescale_factor_max=0.0, Lx_move=0, Lx_change_max=0.0, Lyz_min=0.0, Lyz_max=0.0,
                  Lx_reference_sign=1, seed=12345, device=0, lanes_per_cell=0, cell_lanes=0, shift_every=0,
-                 cells_max_occupancy=-1, cells_mid_occupancy=-1):
+                 cells_max_occupancy=-1, cells_mid_occupancy=-1, x_layers_multiple=0):
         self.L = load_library()
         p = Params()
         self.L.pp_default_params(C.byref(p))
@@ -180,6 +180,7 @@ class Engine:
         p.lanes_per_cell, p.cell_lanes, p.shift_every = lanes_per_cell, cell_lanes, shift_every
         p.cells_max_occupancy = cells_max_occupancy
         p.cells_mid_occupancy = cells_mid_occupancy
+        p.x_layers_multiple = x_layers_multiple
         self.params = p
         self.h = C.c_void_p()
         rc = self.L.pp_create(C.byref(p), C.byref(self.h))

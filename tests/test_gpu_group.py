@@ -70,6 +70,25 @@ def test_virtual_slabs_match_single_engine(pp, n, N, rho, sweeps, chunks):
     g.close()
 
 
+@pytest.mark.parametrize("n,N,rho", [(3, 30000, 0.5), (4, 40000, 0.55)])
+def test_balanced_slabs(pp, n, N, rho):
+    """x_layers_multiple = 2 n: the number of x layers is a multiple of 2 n, every slab owns the same number of them, and a single
+    engine on the same grid follows the same trajectory bit for bit (the grid, not the decomposition, decides the trajectory)."""
+    box, r, m = pp.random_fluid(N, rho, seed=9)
+    params = dict(PARAMS, x_layers_multiple=2 * n)
+    plain = pp.Engine(**PARAMS)
+    plain.upload(box, r, m)
+    nx_plain = plain.observables().n_side[0]
+    plain.close()
+    g = pp.Group(n, **params)
+    o = compare_with_single(pp, g, params, box, r, m, 6)
+    ranges = g.slab_ranges()
+    nx = ranges[0][2]
+    assert nx % (2 * n) == 0 and nx == nx_plain - nx_plain % (2 * n) and o.n_side[0] == nx
+    assert len({x[1] - x[0] for x in ranges}) == 1  # the same number of layers everywhere
+    g.close()
+
+
 @pytest.mark.parametrize("kernel", [dict(lanes_per_cell=1), dict(cells_max_occupancy=1, cells_mid_occupancy=2), dict(cells_max_occupancy=2, cell_lanes=2),
                                     dict(lanes_per_cell=8)])
 def test_virtual_slabs_every_kernel(pp, kernel):

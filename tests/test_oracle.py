@@ -336,7 +336,7 @@ def test_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(pkg.library_path())
     for name in sorted(declared):
         assert hasattr(lib, name), name
-    assert lib.pp_abi_version() == 3
+    assert lib.pp_abi_version() == 4
     assert ctypes.sizeof(pkg.Params) >= 120
 
 
