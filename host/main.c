@@ -293,6 +293,7 @@ int main(int argc, char *argv[]) {
 	if(pph_get_int(in, "Lanes_per_cell", &itmp, 0)) prm.lanes_per_cell = itmp;
 	if(pph_get_int(in, "Shift_every", &itmp, 0)) prm.shift_every = itmp;
 	if(pph_get_int(in, "Lx_reference_sign", &itmp, 0)) prm.Lx_reference_sign = itmp;
+	if(pph_get_int(in, "X_layers_multiple", &itmp, 0)) prm.x_layers_multiple = itmp; /* 2 x GPUs: every slab the same number of cell layers */
 
 	/* GPUs = n: the system is split into n x-slabs, slab k on device GPU_device + k (GPU_devices = a b c ... names them
 	 * explicitly; a device may be listed several times).  One host thread drives all of them (pp_group). */
