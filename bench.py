@@ -8,7 +8,8 @@ A "step" is one MC step of the reference (main.c:119): N_particles attempted rot
 (one 8-colour checkerboard sweep including its share of the cell builds).  The headline workload is the
 same at every GPU count -- BASELINE.json configs[3], N = 4 194 304 at rho = 0.6, NVT -- on one engine at
 --gpus 1 and split into N x-slabs at --gpus N (strong scaling), so the driver's efficiency divides
-like by like.  The one-GPU line also carries, under "configs", the other BASELINE configurations
+like by like (at --gpus N the cell grid has a multiple of 2 N layers along x, pp_params.x_layers_multiple, so that every
+slab holds the same number of layers).  The one-GPU line also carries, under "configs", the other BASELINE configurations
 measured in the same run: N = 65536 (configs[1]), NPT and Lx moves at N = 32768 (configs[2]), the FCC
 crystal at N = 256 000 (configs[4]) and N = 1000 (configs[0]); --workload picks another headline,
 --no-configs drops the extra ones.

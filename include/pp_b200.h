@@ -213,7 +213,7 @@ int pp_reset_kernel_stats(pp_handle *h);
  *     pp_slab_pass_block(1);  last owned layer  -> right neighbour's left halo
  *     pp_slab_sweep_end()
  * Records are 13 doubles (x, y, z, id, orientation[9]); halo views are contiguous slices of the
- * engine's position (double4), orientation (9 doubles) and fixed-point shadow (uint2) arrays.  All
+ * engine's position (double4), orientation (9 doubles) and fixed-point shadow (uint4) arrays.  All
  * pointers returned here are DEVICE pointers. */
 int pp_slab_setup(pp_handle *h, int rank, int world);
 int pp_slab_range(pp_handle *h, int *x0, int *x1, int *nx, int *n_local);
@@ -241,7 +241,7 @@ typedef struct pp_peer_info {
 	unsigned char ipc[64];              /* cudaIpcMemHandle_t of the engine's arena */
 	unsigned long long off_pos[3];      /* byte offsets inside the arena: position buffers (double4) */
 	unsigned long long off_ori[2];      /* orientation buffers (9 doubles per particle) */
-	unsigned long long off_posf;        /* fixed-point shadows (uint2) */
+	unsigned long long off_posf;        /* fixed-point shadows (uint4: box fractions x, y, z + slot) */
 	unsigned long long off_mig[2];      /* migration mailboxes: records from the left / right neighbour */
 	unsigned long long off_ctrl;        /* control words: phases completed by the left / right neighbour, migration flags and counts */
 	long long cap_records;              /* records per mailbox */

@@ -7,7 +7,7 @@
  * serial restatement of this repo's checkerboard sweep (same Philox streams as the CUDA kernel).
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function here against
+ * Parity status: PINNED.  tests/test_oracle.py checks every function here against
  * the unmodified reference built into oracle/_ref/libppref.so, and against the golden vectors in
  * tests/golden/ that were generated from that library (tools/make_golden.py).
  *
