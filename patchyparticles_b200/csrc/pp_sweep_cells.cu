@@ -34,7 +34,10 @@
 
 namespace pp {
 
-constexpr int kCellThreads = 64;
+// one warp per block: 12 blocks per SM at 168 registers and 18 KB of shared memory.  (Two warps per block, six blocks per SM, is the
+// same at every size but 256k, where the finer blocks gain 13 %: a block's slot is free again when ITS cells are done.)
+constexpr int kCellThreads = 32;
+constexpr int kCellBlocksPerSM = 384 / kCellThreads;
 constexpr float kScreenBand = 2e-3f;         // safety band of the FP32 screens (error of the shadow arithmetic < 1e-5)
 constexpr unsigned kNearOld = 0x40u, kNearNew = 0x80u, kIdxMask = 0x3fu;
 
@@ -61,7 +64,7 @@ struct OwnStage {
 	double ori[kMaxOwn * 9];
 };
 
-// shared memory of one block (64 threads) running G lanes per cell
+// shared memory of one block (kCellThreads threads) running G lanes per cell
 template<int G>
 struct CellSmem {
 	uint4 stage[lane_cap(G)][kCellThreads];        // [entry][thread]: shadow of a staged neighbour
@@ -402,7 +405,7 @@ __device__ __forceinline__ void sweep_cells_body(CellSmem<G> &sm, const SimConst
 
 // one configuration alone over one range of the work list
 template<int G>
-__global__ void __launch_bounds__(kCellThreads, 6) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
+__global__ void __launch_bounds__(kCellThreads, kCellBlocksPerSM) k_sweep_cells(const __grid_constant__ SimConst sc, const int *__restrict__ range,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
 		uint4 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
 	__shared__ __align__(16) CellSmem<G> sm;
@@ -420,13 +423,14 @@ union FusedSmem {
 	__device__ FusedSmem() {}
 };
 
-__global__ void __launch_bounds__(kCellThreads, 6) k_sweep_fused(const __grid_constant__ SimConst sc, const int *__restrict__ ranges /* 6 ints */,
+__global__ void __launch_bounds__(kCellThreads, kCellBlocksPerSM) k_sweep_fused(const __grid_constant__ SimConst sc, const int *__restrict__ ranges /* 6 ints */,
 		const int *__restrict__ cell_start, const int *__restrict__ work, const Proposal *__restrict__ proposals, double4 *pos, double *ori,
 		uint4 *posf, Counters *__restrict__ counters, const __grid_constant__ HaloMirror hm) {
 	__shared__ __align__(16) unsigned char raw[sizeof(FusedSmem)];
 	const int b8 = ranges[0], e8 = ranges[1], b4 = ranges[2], e4 = ranges[3], b1 = ranges[4], e1 = ranges[5];
 	const int grid = (int) gridDim.x;
-	int n8 = (e8 - b8 + 7) / 8, n4 = (e4 - b4 + 15) / 16, n1 = (e1 - b1 + 63) / 64;
+	constexpr int k8 = kCellThreads / 8, k4 = kCellThreads / 4, k1 = kCellThreads; // cells per block of each configuration
+	int n8 = (e8 - b8 + k8 - 1) / k8, n4 = (e4 - b4 + k4 - 1) / k4, n1 = (e1 - b1 + k1 - 1) / k1;
 	// shares of a grid that is smaller than the work: crowded cells keep at most a quarter each, the rest goes to the sparse range
 	n8 = min(n8, max(grid / 4, 1));
 	n4 = min(n4, max(grid / 4, 1));
@@ -468,8 +472,8 @@ int launch_sweep_fused(const SimConst &sc, const int *ranges, long long max_item
 	if(max_items < 1) max_items = 1;
 	// worst case: every active cell non-empty and sparse needs max_items / 64 blocks, every one crowded max_items / 8;
 	// typical fluids need about max_items / 40.  The kernel strides when the grid is smaller than the work.
-	long long blocks = (max_items + 15) / 16 + 8;
-	const long long cap = 148ll * 6 * 6;
+	long long blocks = (max_items + kCellThreads / 4 - 1) / (kCellThreads / 4) + 8;
+	const long long cap = 148ll * kCellBlocksPerSM * 6;
 	if(blocks > cap) blocks = cap;
 	k_sweep_fused<<<(unsigned) blocks, kCellThreads, 0, st>>>(sc, ranges, cb.cell_start, cb.work, proposals, pos, ori, cb.posf, counters, hm);
 	return 1;
