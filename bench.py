@@ -43,6 +43,7 @@ WORKLOADS = {
     "256k": dict(N=262144, rho=0.5, T=0.1, kind="fluid", extra={}),
     "512k": dict(N=524288, rho=0.6, T=0.1, kind="fluid", extra={}),
     "1M": dict(N=1048576, rho=0.6, T=0.1, kind="fluid", extra={}),
+    "128k": dict(N=131072, rho=0.6, T=0.1, kind="fluid", extra={}),
     "448k": dict(N=458752, rho=0.6, T=0.1, kind="fluid", extra={}),
     "576k": dict(N=589824, rho=0.6, T=0.1, kind="fluid", extra={}),
     "640k": dict(N=655360, rho=0.6, T=0.1, kind="fluid", extra={}),
@@ -466,7 +467,7 @@ def measure(pkg, args, w, K, W, n_e2e, cpu_budget_s, ctx, headline):
     passes_per_launch = max(int(round(n_passes / max(sweep_launches, 1))), 1)  # 1: a launch per colour pass; 4: a dataflow launch per half sweep
     per_launch_ms = sweep_ms / max(sweep_launches, 1)
     dense = args.cells_max_occupancy < 0 and args.lanes != 1 and 27. * N > 32. * cells[0] * cells[1] * cells[2]  # routing_limits (pp_api.cu)
-    tile_only = (n_local < 150000 and args.cells_max_occupancy < 0 and args.lanes != 1) or min(cells) < 4 or dense
+    tile_only = (n_local < 100000 and args.cells_max_occupancy < 0 and args.lanes != 1) or min(cells) < 4 or dense
     sweep_kernel = ("k_sweep_pass (tile kernel)" if tile_only else
                     "k_sweep_half (the four colour passes of a half sweep in one dataflow launch; 8 / 4 / 1 lanes per cell)" if passes_per_launch == 4 else
                     "k_sweep_fused (8 / 4 / 1 lanes per cell in one launch)")

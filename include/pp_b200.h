@@ -67,7 +67,7 @@ typedef struct pp_params {
 	int cell_lanes;             /* 2, 4, 8 (or -1: one thread): that many lanes per cell for the sparsely populated range (the three ranges then run as
 	                               three launches); 0 or 1: one thread per cell inside the fused launch */
 	int cells_max_occupancy;    /* cells with at most this many particles run on one thread per cell;
-	                               -1 = automatic (3 for N >= 800k, 2 for N >= 400k, 1 for N >= 150k, else 0), 0 = tile kernel only */
+	                               -1 = automatic (3 for N >= 800k, 2 for N >= 400k, 1 for N >= 100k, else 0), 0 = tile kernel only */
 	int shift_every;            /* redraw the random grid shift (and rebuild the cells) every this many sweeps; 0 = default (4) */
 	int cells_mid_occupancy;    /* cells with more particles than cells_max_occupancy and at most this many run on 4 lanes per cell, the
 	                               more crowded ones on 8; -1 = automatic */

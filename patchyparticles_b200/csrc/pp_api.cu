@@ -178,8 +178,8 @@ void routing_limits(const pp_handle *h, int *m1, int *m2) {
 		// there (FCC at N = 256000: 4.8e8 against 2.2e8 attempts/s, profiles/README.md)
 		if(h->n_cells > 0 && 27. * (double) h->N > (double) kCellsNbCap * (double) h->n_cells) return;
 		// measured on B200 (profiles/README.md)
-		*m1 = (h->N >= 800000) ? 3 : ((h->N >= 400000) ? 2 : ((h->N >= 150000) ? 1 : 0));
-		*m2 = (h->N >= 800000) ? 3 : ((h->N >= 400000) ? 3 : ((h->N >= 150000) ? 2 : 0));
+		*m1 = (h->N >= 800000) ? 3 : ((h->N >= 400000) ? 2 : ((h->N >= 100000) ? 1 : 0));
+		*m2 = (h->N >= 800000) ? 3 : ((h->N >= 400000) ? 3 : ((h->N >= 100000) ? 2 : 0));
 		if(h->prm.cells_mid_occupancy >= 0 && *m1 > 0) *m2 = h->prm.cells_mid_occupancy;
 	}
 	if(*m2 < *m1) *m2 = *m1;
