@@ -23,8 +23,9 @@
 //                 1 - 2e-3 (squared) to a neighbour is rejected on the spot, a pair is a candidate when its
 //                 squared distance is below r_cut^2 + 2e-3 (the shadow arithmetic is good to 1e-5, so no pair the
 //                 FP64 test would put inside the shell, or flag as overlapping, is ever dropped);
-//              2. FP32 orientation screen of the candidates (own matrix only): most pairs in the
-//                 shell cannot bond because no patch of the moved particle points at them;
+//              2. FP32 orientation screen of the candidates: most pairs in the shell cannot bond because no patch of the
+//                 moved particle points at them (own matrix only); for the few that are left, the same screen from the
+//                 neighbour's matrix -- a bond needs a patch of each pointing at the other (MC.c:249-259);
 //              3. FP64, reference operation order, on what is left: overlap of the new position
 //                 (MC.c:240), shell test (MC.c:241), orientation tests (MC.c:249-261);
 //              4. Metropolis rule (MC.c:332), write-back of position, orientation, shadow.
