@@ -535,6 +535,60 @@ static double u32_to_unit(uint32_t x) {
 	return ((double) x + 0.5) * (1.0 / 4294967296.0);
 }
 
+/* ------------------------------------------------------------------ neighbour queries of the cluster moves */
+/* what AVB's _set_neighbours (avb.c:43-75) collects for particle i: the neighbour bonded through each patch (MC_interact's onp,
+ * MC.c:249-261), walking the 27 cells in the reference's order; returns the number of bonded neighbours.  mode 1: the particles
+ * with dist2 < kf_sqr_rcut (vmmc.c:178) into list[max_nb] instead. */
+int ppo_neighbour_query(ppo_system *s, int i, int mode, int max_nb, int *list) {
+	int idx[3], j, k, l, n = 0, a;
+	const double *rp = s->r + 3 * i, *pp = s->patches + 12 * i;
+	for(a = 0; a < (mode == 0 ? 4 : max_nb); a++) list[a] = -1;
+	ppo_cell_coords(rp, s->box, s->n_side, idx);
+	for(j = -1; j < 2; j++) {
+		int cx = (idx[0] + j + s->n_side[0]) % s->n_side[0];
+		for(k = -1; k < 2; k++) {
+			int cy = (idx[1] + k + s->n_side[1]) % s->n_side[1];
+			for(l = -1; l < 2; l++) {
+				int cz = (idx[2] + l + s->n_side[2]) % s->n_side[2];
+				int c = (cx * s->n_side[1] + cy) * s->n_side[2] + cz;
+				for(a = s->cell_start[c]; a < s->cell_start[c + 1]; a++) {
+					const int q = s->cell_items[a];
+					if(q == i) continue;
+					const double *rq = s->r + 3 * q, *pq = s->patches + 12 * q;
+					double d[3] = {rq[0] - rp[0], rq[1] - rp[1], rq[2] - rp[2]};
+					int m, u, v, onp = -1;
+					for(m = 0; m < 3; m++) d[m] -= s->box[m] * rint(d[m] / s->box[m]);
+					const double d2 = dot3(d, d);
+					if(mode == 1) {
+						if(d2 < s->sqr_rcut) {
+							if(n < max_nb) list[n] = q;
+							n++;
+						}
+						continue;
+					}
+					if(d2 < 1. || d2 >= s->sqr_rcut) continue;
+					const double norm = sqrt(d2);
+					d[0] /= norm;
+					d[1] /= norm;
+					d[2] /= norm;
+					for(u = 0; u < 4 && onp < 0; u++)
+						if(dot3(d, pp + 3 * u) > s->kf_cosmax)
+							for(v = 0; v < 4; v++)
+								if(-dot3(d, pq + 3 * v) > s->kf_cosmax) {
+									onp = u;
+									break;
+								}
+					if(onp >= 0) {
+						list[onp] = q; /* avb.c:64: the last one in the walk keeps the patch */
+						n++;
+					}
+				}
+			}
+		}
+	}
+	return n;
+}
+
 /* ------------------------------------------------------------------ grand-canonical insertion / removal */
 /* random_vector_on_sphere (utils.c:115-131) from a recorded stream */
 static void gc_sphere(const double *u, int n_u, int *used, double *res) {

@@ -75,6 +75,10 @@ int ppo_volume_move(ppo_system *s, double P, double rescale_factor_max, double u
 int ppo_Lx_move(ppo_system *s, double Lx_change_max, double Lyz_min, double Lyz_max, int faithful_sign,
 		double u_lx, double u_acc, long long *energy_bonds, int *overlap_out);
 
+/* neighbour queries of the cluster moves: mode 0, _set_neighbours (avb.c:43-75): list[4] = neighbour bonded through each patch, returns
+ * the number of bonded neighbours; mode 1, the range test of _populate_possible_links (vmmc.c:178): list[max_nb] = particles in range */
+int ppo_neighbour_query(ppo_system *s, int i, int mode, int max_nb, int *list);
+
 /* MC_add_remove (MC.c:342-448) given its uniforms in the reference's draw order; returns 2 (insertion), 3 (removal) or -1 */
 int ppo_add_remove(ppo_system *s, double z, int n_min, int n_max, const double *u, int n_u, int *accepted, int *used, long long *energy_bonds);
 

@@ -74,6 +74,7 @@ def port_lib():
                                   C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
     L.ppo_Lx_move.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
                               C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+    L.ppo_neighbour_query.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip]
     L.ppo_add_remove.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_longlong)]
     L.ppo_sweep.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_double,
@@ -200,6 +201,17 @@ class PortSystem:
         acc = self.L.ppo_Lx_move(self.h, Lx_change_max, Lyz_min, Lyz_max, int(faithful_sign), u_lx, u_acc,
                                  C.byref(b), C.byref(ov))
         return int(acc), int(b.value), int(ov.value)
+
+    def patch_neighbours(self, i):
+        """_set_neighbours (avb.c:43-75) -> (neighbour per patch, number of bonded neighbours)"""
+        nb = np.full(4, -1, dtype=np.int32)
+        n = self.L.ppo_neighbour_query(self.h, int(i), 0, 4, nb)
+        return nb, int(n)
+
+    def range_neighbours(self, i, max_nb=32):
+        nb = np.full(max_nb, -1, dtype=np.int32)
+        n = self.L.ppo_neighbour_query(self.h, int(i), 1, int(max_nb), nb)
+        return int(n), nb
 
     def add_remove(self, z, n_min, n_max, uniforms, bonds):
         """MC_add_remove (MC.c:342-448) with recorded uniforms -> (kind, accepted, uniforms consumed, N, running bonds)"""

@@ -435,3 +435,23 @@ def test_port_gc_moves_golden(oracle):
     r, m = p.state()
     assert np.array_equal(r, g["r_final"]) and np.array_equal(m, g["orient_final"])
     assert p.total_bonds() == (bonds, 0)
+
+
+def test_port_neighbour_queries_golden(oracle):
+    """The restated neighbour queries (avb.c:43-75, vmmc.c:178) against the reference's MC_interact over all pairs."""
+    g = load_golden("neighbour_queries")
+    delta, T = g["params"]
+    N = len(g["r"])
+    for tag, cosmax in (("narrow", 0.98), ("wide", 0.8)):
+        p = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=cosmax, temperature=T)
+        cnt, q, onp = g[f"{tag}_count"], g[f"{tag}_q"], g[f"{tag}_onp"]
+        for i in range(N):
+            nb, num = p.patch_neighbours(i)
+            assert num == cnt[i]
+            for patch in range(4):
+                on_patch = [int(q[i, k]) for k in range(cnt[i]) if onp[i, k] == patch]
+                assert (nb[patch] == -1) if not on_patch else (nb[patch] in on_patch)
+    p = oracle.PortSystem(g["box"], g["r"], g["orient"], kf_delta=delta, kf_cosmax=0.98, temperature=T)
+    for i in range(0, N, 7):
+        n, nb = p.range_neighbours(i, 24)
+        assert n == g["range_count"][i] and sorted(nb[:n].tolist()) == sorted(g["range_nb"][i, :n].tolist())
