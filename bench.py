@@ -583,7 +583,7 @@ def measure(pkg, args, w, K, W, n_e2e, cpu_budget_s, ctx, headline):
         "pair_checks_per_s_l2_warm": pair_checks_per_s,
         "cpu_baseline": cpu,
         "e2e": {"value": n_e2e * attempts_per_step / e2e_s, "unit": "attempts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "step": "upload (pinned host configuration -> HBM, cell build) + one MC step + observables read-back", "steps": n_e2e},
+                "step": "upload (pinned host configuration -> HBM) + one MC step (cell build on the step's shifted grid, proposals, eight colour passes) + observables read-back", "steps": n_e2e},
         "e2e_roundtrip": {"value": n_rt * attempts_per_step / rt_s, "unit": "attempts/s", "h2d_bytes_per_step": h2d,
                           "d2h_bytes_per_step": int(r_host.nbytes + m_host.nbytes),
                           "step": "upload + one MC step + pp_download of every position and orientation", "steps": n_rt},
