@@ -58,7 +58,7 @@ MELT_SWEEPS = 300  # hard-sphere sweeps that turn the thinned lattice of patchy_
 # dram__bytes_read.sum + dram__bytes_write.sum per colour-pass launch from the committed ncu captures (profiles/), by
 # (workload, GPUs); absent where no capture of that shape is committed
 SWEEP_TRAFFIC = {
-    ("4M", 1): 584.9e6,    # profiles/r02m_launches_4M.txt: k_sweep_fused 503.7 MB read + 81.2 MB written per launch (524288 trials)
+    ("4M", 1): 587.4e6,    # profiles/r03u_launches_4M.txt: k_sweep_fused 541.3 MB read + 46.1 MB written per launch (524288 trials)
     ("512k", 1): 39.0e6,   # profiles/r02n_sweep_fused_512k_full.txt: 38.7 MB read + 0.3 MB written per launch (65536 trials), state resident in L2
     ("fcc256k", 1): 37.2e6,  # profiles/r02y_fcc_and_slab_upload.txt (capture of the fused launch on the crystal; the tile kernel now runs it)
 }
